@@ -1,0 +1,153 @@
+/*
+ * jpegenc_b200.h -- C ABI of the B200-native JPEG encode path (drop-in for the encode path of
+ * vstroebel/jpeg-encoder v0.7.0). Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * The reference has no FFI of its own. The cut is made at
+ * `Encoder::encode_image_internal` (/root/reference/src/encoder.rs:517-567): everything between
+ * "packed pixels in" and "JFIF bytes out". A Rust `Encoder<W>` shim keeps the crate's public API
+ * (Encoder::new, the setters, encode) and forwards to these entry points; the binding a maintainer
+ * would add is shown in INTEGRATION.md. include/jpeg_encoder.hpp is the same mirror in C++ and
+ * jpeg_encoder_b200/encoder.py in Python (ctypes).
+ *
+ * Output bytes are identical to the reference's for the same input and settings. There is no CPU
+ * fallback: every entry point fails with JPGB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef JPEGENC_B200_H
+#define JPEGENC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ColorType -- /root/reference/src/encoder.rs:72-99 (same order) */
+enum {
+    JPGB_LUMA = 0, JPGB_RGB = 1, JPGB_RGBA = 2, JPGB_BGR = 3, JPGB_BGRA = 4,
+    JPGB_YCBCR = 5, JPGB_CMYK = 6, JPGB_CMYK_AS_YCCK = 7, JPGB_YCCK = 8
+};
+
+/* QuantizationTableType -- src/quantization.rs:8-59 (index() order), 9 = Custom(Box<[u16;64]>) */
+enum {
+    JPGB_QT_DEFAULT = 0, JPGB_QT_FLAT = 1, JPGB_QT_CUSTOM_MS_SSIM = 2, JPGB_QT_CUSTOM_PSNR_HVS = 3,
+    JPGB_QT_IMAGE_MAGICK = 4, JPGB_QT_KLEIN_SILVERSTEIN_CARNEY = 5, JPGB_QT_DENTAL_XRAYS = 6,
+    JPGB_QT_VISUAL_DETECTION_MODEL = 7, JPGB_QT_IMPROVED_DETECTION_MODEL = 8, JPGB_QT_CUSTOM = 9
+};
+
+/* EncodingError -- src/error.rs:6-28, plus the CUDA failure the reference cannot have */
+enum {
+    JPGB_OK = 0,
+    JPGB_ERR_BAD_IMAGE_DATA = 1,     /* BadImageData { length, required }   src/encoder.rs:447-454 */
+    JPGB_ERR_ZERO_DIMENSIONS = 2,    /* ZeroImageDimensions                 src/encoder.rs:521-526 */
+    JPGB_ERR_INVALID_APP_SEGMENT = 3,/* InvalidAppSegment(nr)               src/encoder.rs:375-376 */
+    JPGB_ERR_APP_SEGMENT_TOO_LARGE = 4, /* AppSegmentTooLarge(len)          src/encoder.rs:377-378 */
+    JPGB_ERR_BAD_PARAMS = 5,         /* what the reference rejects by panic/assert (scan count, sampling) */
+    JPGB_ERR_SINK = 6,               /* IoError / Write: the sink callback returned non-zero */
+    JPGB_ERR_NOMEM = 7,
+    JPGB_ERR_CUDA = 8,               /* no usable sm_100 device, or a CUDA call failed */
+    JPGB_ERR_HUFFMAN = 9             /* optimized code longer than 32 bits (the reference panics) */
+};
+
+/* one `add_app_segment(nr, data)` entry, src/encoder.rs:374-383. ICC/EXIF are expanded into
+ * these by the caller exactly as add_icc_profile / add_exif_metadata do (:392-435). */
+typedef struct jpgb_app_segment {
+    uint8_t nr;            /* 1..15 */
+    const uint8_t *data;
+    uint32_t len;          /* <= 65533 */
+} jpgb_app_segment;
+
+/* The state of an `Encoder<W>` at the moment `encode` is called (src/encoder.rs:213-231).
+ * Caller-owned, read-only during the call. */
+typedef struct jpgb_params {
+    uint16_t width, height;        /* encode(data, width, height, ..)                  :440-446 */
+    uint8_t color_type;            /* JPGB_LUMA .. JPGB_YCCK                            :72-99  */
+    uint8_t quality;               /* Encoder::new(w, quality); clamped 1..=100         :239    */
+    uint8_t sampling;              /* SamplingFactor as (h<<4)|v; alias bit 0x80 ignored :120-176 */
+    uint8_t qtable_kind[2];        /* [luma, chroma] JPGB_QT_*                          :300-306 */
+    uint16_t qtable_custom[2][64]; /* natural (row-major) order, used when kind == JPGB_QT_CUSTOM */
+    uint8_t progressive_scans;     /* 0 = baseline; 2..=64 = set_progressive_scans      :317-335 */
+    uint8_t optimize_huffman;      /* set_optimized_huffman_tables                      :357-359 */
+    uint16_t restart_interval;     /* 0 = off; set_restart_interval                     :345-347 */
+    uint8_t density_unit;          /* 0 PixelAspectRatio, 1 Inches, 2 Centimeters  src/writer.rs:16-59 */
+    uint16_t density_x, density_y; /* default (1,1) with unit 0 */
+    uint32_t n_app;
+    const jpgb_app_segment *apps;  /* insertion order */
+} jpgb_params;
+
+/* Fill `p` with what `Encoder::new(w, quality)` sets (src/encoder.rs:239-275): default tables,
+ * F_2_2 below quality 90 else F_1_1, density (1,1) unit 0, everything else off. */
+void jpgb_params_default(jpgb_params *p, uint8_t quality);
+
+/* An encoder context bound to one CUDA device: its stream, scratch buffers and pinned staging.
+ * Not thread-safe; create one per host thread (the reference's Encoder is likewise single-owner).
+ * `cuda_stream` may be NULL (the context creates its own) or a cudaStream_t the work is queued on. */
+typedef struct jpgb_encoder jpgb_encoder;
+int jpgb_encoder_create(int device, void *cuda_stream, jpgb_encoder **out);
+void jpgb_encoder_destroy(jpgb_encoder *enc);
+const char *jpgb_last_error(const jpgb_encoder *enc); /* text of the last failure on this context */
+
+/* Encoder::encode (src/encoder.rs:440-503): host pixels in, complete JFIF file out.
+ * `pixels` is packed, row stride width*bpp; bytes past width*height*bpp are ignored (Q22).
+ * On success *out is a library-owned buffer (release with jpgb_free). */
+int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len,
+                uint8_t **out, size_t *out_len);
+void jpgb_free(void *buf);
+
+/* Same, delivering the bytes through a JfifWrite::write_all-style callback
+ * (src/writer.rs:76-82). A non-zero return from `write_all` aborts with JPGB_ERR_SINK. */
+typedef int (*jpgb_write_all_fn)(void *user, const uint8_t *buf, size_t len);
+int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len,
+                        jpgb_write_all_fn write_all, void *user);
+
+/* Batch of `n` images of identical geometry and settings (BASELINE config 3; no reference
+ * equivalent -- the crate is called once per image). Host memory in and out.
+ * pixels[i] points at image i. outs[i]/out_lens[i] receive library-owned buffers (jpgb_free). */
+int jpgb_encode_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels,
+                      size_t len_each, uint32_t n, uint8_t **outs, size_t *out_lens);
+
+/* Device-resident batch: `d_pixels` is device memory holding n images `image_stride` bytes apart.
+ * The n files are written back to back into device memory owned by the context; on return
+ * *d_files points at it and offsets[0..n] (host array of n+1) delimits file i as
+ * [offsets[i], offsets[i+1]). The buffer stays valid until the next call on this context.
+ * This is the path bench.py times for the device-resident `value`. */
+int jpgb_encode_batch_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels,
+                             size_t image_stride, uint32_t n, const void **d_files, uint64_t *offsets);
+
+/* ---- stage-level entry points (parity tests and roofline timing) ------------------------------ */
+
+/* Block-grid geometry of the coefficient buffer for `p`: per component the MCU-padded grid
+ * (blocks_w x blocks_h, raster order, 64 i16 zig-zag coefficients each; Q9, Q14) and the block
+ * offset of the component inside one image's buffer. Returns the number of components. */
+typedef struct jpgb_coef_layout {
+    uint32_t n_components;
+    uint32_t blocks_w[4], blocks_h[4]; /* padded grid = mcu_cols*H_c x mcu_rows*V_c */
+    uint32_t true_w[4], true_h[4];     /* grid encode_blocks walks (src/encoder.rs:1012-1025) */
+    uint64_t block_offset[4];          /* first block of the component, in blocks */
+    uint64_t blocks_per_image;
+} jpgb_coef_layout;
+int jpgb_coef_layout_for(const jpgb_params *p, jpgb_coef_layout *layout);
+
+/* Stage A only: colour conversion + decimation + level shift + fDCT + quantization
+ * (image_buffer.rs, encoder.rs:1222-1272, fdct.rs, quantization.rs) on device memory.
+ * d_coef must hold n * blocks_per_image * 64 int16. Asynchronous on the context's stream. */
+int jpgb_stage_a_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels,
+                        size_t image_stride, uint32_t n, void *d_coef);
+
+/* Per-stage device time of the last jpgb_encode* call on this context, in milliseconds, measured
+ * with CUDA events on the context's stream (enabled with jpgb_encoder_set_timing).
+ * stage index: 0 = colour+DCT+quant kernel, 1 = histogram + table build (optimized only),
+ * 2 = symbol sizing + prefix sums, 3 = bit emission, 4 = byte stuffing + scatter, 5 = H2D, 6 = D2H. */
+#define JPGB_N_STAGES 7
+void jpgb_encoder_set_timing(jpgb_encoder *enc, int enabled);
+int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]);
+
+/* number of kernel launches issued by the last jpgb_encode* / jpgb_stage_a_device call */
+uint32_t jpgb_encoder_last_launch_count(const jpgb_encoder *enc);
+
+const char *jpgb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEGENC_B200_H */

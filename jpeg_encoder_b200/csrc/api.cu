@@ -1,0 +1,500 @@
+// C ABI (include/jpegenc_b200.h) and the per-call orchestration of the device pipeline.
+// The product path has no CPU fallback: without a usable sm_100 device every entry point
+// returns JPGB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jpegenc_b200.h"
+#include "host.h"
+#include "kernels.h"
+
+using namespace jpgb;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256; // grow-only with slack: steady-state calls never allocate
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct jpgb_encoder {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
+        scan_tmp, hist;
+    PinnedBuf h_small, h_hist, h_tables;
+    bool timing = false;
+    cudaEvent_t ev[JPGB_N_STAGES + 1][2] = {};
+    bool ev_used[JPGB_N_STAGES] = {};
+    float last_ms[JPGB_N_STAGES] = {};
+    bool have_timing = false;
+    uint32_t launches = 0;
+    // result of the last device batch
+    uint64_t out_total = 0;
+};
+
+namespace {
+
+int fail(jpgb_encoder *e, int code, const std::string &msg) {
+    if (e) e->err = msg;
+    return code;
+}
+int fail_cuda(jpgb_encoder *e, cudaError_t ce, const char *what) {
+    return fail(e, JPGB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+}
+#define CK(call, what)                                        \
+    do {                                                      \
+        cudaError_t ce__ = (call);                            \
+        if (ce__ != cudaSuccess) return fail_cuda(enc, ce__, what); \
+    } while (0)
+
+struct StageTimer {
+    jpgb_encoder *enc;
+    int stage;
+    StageTimer(jpgb_encoder *e, int s) : enc(e), stage(s) {
+        if (enc->timing) {
+            if (!enc->ev_used[stage]) cudaEventRecord(enc->ev[stage][0], enc->stream);
+        }
+    }
+    ~StageTimer() {
+        if (enc->timing) {
+            cudaEventRecord(enc->ev[stage][1], enc->stream);
+            enc->ev_used[stage] = true;
+        }
+    }
+};
+
+void timing_begin(jpgb_encoder *enc) {
+    for (int i = 0; i < JPGB_N_STAGES; ++i) enc->ev_used[i] = false;
+    enc->have_timing = false;
+    enc->launches = 0;
+}
+void timing_end(jpgb_encoder *enc) {
+    if (!enc->timing) return;
+    cudaStreamSynchronize(enc->stream);
+    for (int i = 0; i < JPGB_N_STAGES; ++i) {
+        enc->last_ms[i] = 0.f;
+        if (enc->ev_used[i]) cudaEventElapsedTime(&enc->last_ms[i], enc->ev[i][0], enc->ev[i][1]);
+    }
+    enc->have_timing = true;
+}
+
+int validate_and_plan(jpgb_encoder *enc, const jpgb_params *p, size_t len_each, Plan &plan) {
+    if (!p) return fail(enc, JPGB_ERR_BAD_PARAMS, "null params");
+    if (p->color_type > JPGB_YCCK) return fail(enc, JPGB_ERR_BAD_PARAMS, "bad color_type");
+    const size_t required = (size_t)p->width * p->height * (size_t)bytes_per_pixel(p->color_type);
+    if (len_each < required) { // BadImageData comes first, encoder.rs:447-454
+        char m[128];
+        snprintf(m, sizeof(m), "Image data too small for dimensions and color_type: %zu need at least %zu", len_each, required);
+        return fail(enc, JPGB_ERR_BAD_IMAGE_DATA, m);
+    }
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return fail(enc, rc, rc == JPGB_ERR_ZERO_DIMENSIONS ? "Image dimensions must be non zero" : "invalid parameters");
+    return JPGB_OK;
+}
+
+// The whole device pipeline for `n` device-resident images. On success the files lie back to back
+// in enc->out and `offsets` (host, n + 1) delimits them.
+int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, size_t image_stride, uint32_t n,
+                  std::vector<uint64_t> &offsets) {
+    cudaStream_t st = enc->stream;
+    DevPlan hp;
+    plan.fill_device_plan(hp);
+    StageAParams ap;
+    plan.fill_stage_a(ap);
+
+    const uint64_t n_blocks = plan.blocks_per_image * n;
+    const uint64_t n_visits = plan.visits_per_image * n;
+    const uint64_t n_segs = (uint64_t)plan.segs_per_image * n;
+
+    CK(enc->coef.reserve(n_blocks * 128), "alloc coefficients");
+    CK(enc->plan.reserve(sizeof(DevPlan)), "alloc plan");
+    CK(cudaMemcpyAsync(enc->plan.p, &hp, sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
+
+    // ---- stage A ----
+    {
+        StageTimer t(enc, 0);
+        ap.pixels = d_pixels;
+        ap.coef = enc->coef.as<int16_t>();
+        ap.image_stride = image_stride;
+        CK(launch_stage_a(ap, n, st), "stage A launch");
+        enc->launches += 1;
+    }
+
+    // ---- Huffman tables: Annex K.3 defaults, or built from this image's symbol histogram ----
+    const bool optimized = plan.p.optimize_huffman != 0;
+    const uint32_t n_huff = optimized ? n : 1;
+    std::vector<HuffTable> tables(n_huff * 4);
+    for (uint32_t i = 0; i < n_huff; ++i) default_huffman_tables(reinterpret_cast<HuffTable(*)[2]>(&tables[i * 4]));
+    if (optimized) {
+        StageTimer t(enc, 1);
+        const size_t hist_words = (size_t)n * 2 * 2 * 257;
+        CK(enc->hist.reserve(hist_words * 4), "alloc histogram");
+        CK(enc->h_hist.reserve(hist_words * 4), "alloc histogram (host)");
+        CK(cudaMemsetAsync(enc->hist.p, 0, hist_words * 4, st), "clear histogram");
+        CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
+        enc->launches += n;
+        CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_words * 4, cudaMemcpyDeviceToHost, st), "download histogram");
+        CK(cudaStreamSynchronize(st), "histogram sync");
+        const int max_tables = plan.ncomp < 2 ? plan.ncomp : 2; // encoder.rs:1089
+        for (uint32_t i = 0; i < n; ++i)
+            for (int tb = 0; tb < max_tables; ++tb)
+                for (int cls = 0; cls < 2; ++cls) {
+                    uint32_t freq[257];
+                    std::memcpy(freq, enc->h_hist.as<uint32_t>() + ((size_t)i * 4 + tb * 2 + cls) * 257, sizeof(freq));
+                    freq[256] = 1; // reserved code point, encoder.rs:1092-1095
+                    if (!tables[i * 4 + tb * 2 + cls].set_optimized(freq)) return fail(enc, JPGB_ERR_HUFFMAN, "optimized code longer than 32 bits");
+                }
+    }
+
+    // ---- per-image file header: SOI/APPn prefix, SOF/DQT/DHT/DRI, first SOS (Q21) ----
+    std::vector<std::vector<uint8_t>> headers(n_huff);
+    size_t hdr_stride = 0;
+    for (uint32_t i = 0; i < n_huff; ++i) {
+        std::vector<uint8_t> &h = headers[i];
+        h = plan.prefix;
+        plan.frame_header(reinterpret_cast<const HuffTable(*)[2]>(&tables[i * 4]), h);
+        h.insert(h.end(), plan.scans[0].sos.begin(), plan.scans[0].sos.end());
+        hdr_stride = std::max(hdr_stride, h.size());
+    }
+    hdr_stride = (hdr_stride + 15) & ~(size_t)15;
+    {
+        const size_t tab_bytes = (size_t)n_huff * kHuffWordsPerImage * 4, hdr_bytes = (size_t)n_huff * hdr_stride, len_bytes = (size_t)n_huff * 4;
+        CK(enc->h_tables.reserve(tab_bytes + hdr_bytes + len_bytes), "alloc tables (host)");
+        uint8_t *hb = enc->h_tables.as<uint8_t>();
+        for (uint32_t i = 0; i < n_huff; ++i) {
+            for (int t = 0; t < 4; ++t) std::memcpy(hb + ((size_t)i * 4 + t) * 1024, tables[i * 4 + t].lookup, 1024);
+            std::memcpy(hb + tab_bytes + (size_t)i * hdr_stride, headers[i].data(), headers[i].size());
+            reinterpret_cast<uint32_t *>(hb + tab_bytes + hdr_bytes)[i] = (uint32_t)headers[i].size();
+        }
+        CK(enc->huff.reserve(tab_bytes), "alloc huffman tables");
+        CK(enc->hdr.reserve(hdr_bytes), "alloc headers");
+        CK(enc->hdr_len.reserve(len_bytes), "alloc header lengths");
+        CK(cudaMemcpyAsync(enc->huff.p, hb, tab_bytes, cudaMemcpyHostToDevice, st), "upload huffman tables");
+        CK(cudaMemcpyAsync(enc->hdr.p, hb + tab_bytes, hdr_bytes, cudaMemcpyHostToDevice, st), "upload headers");
+        CK(cudaMemcpyAsync(enc->hdr_len.p, hb + tab_bytes + hdr_bytes, len_bytes, cudaMemcpyHostToDevice, st), "upload header lengths");
+    }
+
+    // ---- symbol sizing and the two prefix sums ----
+    CK(enc->nbits.reserve(n_visits * 4), "alloc nbits");
+    CK(enc->bitpos.reserve((n_visits + 1) * 8), "alloc bitpos");
+    CK(enc->seglen.reserve(n_segs * 4), "alloc seglen");
+    CK(enc->segpos.reserve((n_segs + 1) * 8), "alloc segpos");
+    CK(enc->scan_tmp.reserve(scan_tmp_bytes(n_visits > n_segs ? n_visits : n_segs)), "alloc scan scratch");
+    CK(enc->h_small.reserve(64 + (size_t)(n + 1) * 8), "alloc readback");
+
+    EntropyBuffers b{};
+    b.plan = enc->plan.as<DevPlan>();
+    b.coef = enc->coef.as<int16_t>();
+    b.huff = enc->huff.as<uint32_t>();
+    b.huff_per_image = optimized ? 1 : 0;
+    b.nbits = enc->nbits.as<uint32_t>();
+    b.bitpos = enc->bitpos.as<unsigned long long>();
+    b.seglen = enc->seglen.as<uint32_t>();
+    b.segpos = enc->segpos.as<unsigned long long>();
+    b.hdr_len = enc->hdr_len.as<uint32_t>();
+    b.hdr = enc->hdr.as<uint8_t>();
+    b.hdr_stride = (uint32_t)hdr_stride;
+    b.scan_tmp = enc->scan_tmp.p;
+
+    uint64_t ubytes = 0;
+    {
+        StageTimer t(enc, 2);
+        CK(launch_symbol_sizes(b, hp, n, st), "symbol size launch");
+        CK(launch_exclusive_scan(b.nbits, b.bitpos, n_visits, b.scan_tmp, st, &enc->launches), "bit position scan");
+        CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
+        CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches), "segment position scan");
+        enc->launches += 2;
+        CK(cudaMemcpyAsync(enc->h_small.p, b.segpos + n_segs, 8, cudaMemcpyDeviceToHost, st), "read stream size");
+    }
+    CK(cudaStreamSynchronize(st), "sizing sync");
+    ubytes = *enc->h_small.as<uint64_t>();
+
+    // ---- bit emission into the unstuffed stream ----
+    const uint64_t n_chunks = (ubytes + kStuffChunk - 1) / kStuffChunk;
+    CK(enc->ustream.reserve(((ubytes + 15) & ~(uint64_t)15) + 64), "alloc unstuffed stream");
+    CK(enc->raw_mask.reserve(((ubytes + 31) / 32 + 2) * 4), "alloc raw mask");
+    CK(enc->ffcount.reserve((n_chunks + 1) * 4), "alloc ff counts");
+    CK(enc->ffpos.reserve((n_chunks + 2) * 8), "alloc ff positions");
+    CK(enc->scan_tmp.reserve(scan_tmp_bytes(n_chunks)), "alloc scan scratch");
+    CK(enc->file_off.reserve((size_t)(n + 1) * 8), "alloc file offsets");
+    b.ustream = enc->ustream.as<uint8_t>();
+    b.raw_mask = enc->raw_mask.as<uint32_t>();
+    b.ffcount = enc->ffcount.as<uint32_t>();
+    b.ffpos = enc->ffpos.as<unsigned long long>();
+    b.file_off = enc->file_off.as<unsigned long long>();
+    b.scan_tmp = enc->scan_tmp.p;
+    {
+        StageTimer t(enc, 3);
+        CK(launch_zero_ustream(b, n_segs, st), "zero stream launch");
+        CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
+        CK(launch_emit_bits(b, hp, n, st), "emit launch");
+        enc->launches += 3;
+    }
+    // ---- 0xFF stuffing: count, scan, scatter ----
+    {
+        StageTimer t(enc, 4);
+        CK(launch_count_ff(b, ubytes, st), "count ff launch");
+        CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches), "ff scan");
+        enc->launches += 1;
+        CK(cudaMemcpyAsync(enc->h_small.p, b.ffpos + n_chunks, 8, cudaMemcpyDeviceToHost, st), "read ff total");
+    }
+    CK(cudaStreamSynchronize(st), "stuffing sync");
+    const uint64_t total = ubytes + *enc->h_small.as<uint64_t>();
+    CK(enc->out.reserve(total + 64), "alloc output");
+    b.out = enc->out.as<uint8_t>();
+    {
+        StageTimer t(enc, 4);
+        CK(launch_stuff_scatter(b, ubytes, st), "scatter launch");
+        CK(launch_file_offsets(b, hp, n, ubytes, st), "file offsets launch");
+        enc->launches += 2;
+        CK(cudaMemcpyAsync(enc->h_small.p, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
+    }
+    CK(cudaStreamSynchronize(st), "final sync");
+    offsets.assign(enc->h_small.as<uint64_t>(), enc->h_small.as<uint64_t>() + n + 1);
+    enc->out_total = total;
+    if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
+    return JPGB_OK;
+}
+
+int encode_host_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels, size_t len_each, uint32_t n,
+                      uint8_t **outs, size_t *out_lens) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!pixels || !outs || !out_lens || n == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    for (uint32_t i = 0; i < n; ++i) outs[i] = nullptr, out_lens[i] = 0;
+    Plan plan;
+    int rc = validate_and_plan(enc, p, len_each, plan);
+    if (rc != JPGB_OK) return rc;
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    timing_begin(enc);
+    const size_t img_bytes = (size_t)plan.p.width * plan.p.height * plan.bpp;
+    const size_t stride = (img_bytes + 255) & ~(size_t)255;
+    CK(enc->pixels.reserve(stride * n), "alloc pixels");
+    {
+        StageTimer t(enc, 5);
+        for (uint32_t i = 0; i < n; ++i)
+            CK(cudaMemcpyAsync(enc->pixels.as<uint8_t>() + stride * i, pixels[i], img_bytes, cudaMemcpyHostToDevice, enc->stream), "upload pixels");
+    }
+    std::vector<uint64_t> off;
+    rc = encode_device(enc, plan, enc->pixels.as<uint8_t>(), stride, n, off);
+    if (rc != JPGB_OK) return rc;
+    {
+        StageTimer t(enc, 6);
+        for (uint32_t i = 0; i < n; ++i) {
+            const size_t sz = (size_t)(off[i + 1] - off[i]);
+            outs[i] = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
+            if (!outs[i]) {
+                for (uint32_t k = 0; k < i; ++k) std::free(outs[k]), outs[k] = nullptr;
+                return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
+            }
+            out_lens[i] = sz;
+            CK(cudaMemcpyAsync(outs[i], enc->out.as<uint8_t>() + off[i], sz, cudaMemcpyDeviceToHost, enc->stream), "download file");
+        }
+    }
+    CK(cudaStreamSynchronize(enc->stream), "download sync");
+    timing_end(enc);
+    return JPGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void jpgb_params_default(jpgb_params *p, uint8_t quality) {
+    std::memset(p, 0, sizeof(*p));
+    p->quality = quality;
+    p->sampling = quality < 90 ? 0x22 : 0x11; // encoder.rs:256-260
+    p->density_unit = 0;                       // PixelDensity::default, writer.rs:37-45
+    p->density_x = p->density_y = 1;
+}
+
+int jpgb_encoder_create(int device, void *cuda_stream, jpgb_encoder **out) {
+    if (!out) return JPGB_ERR_BAD_PARAMS;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return JPGB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JPGB_ERR_CUDA;
+    if (prop.major != 10) return JPGB_ERR_CUDA; // kernels are built for sm_100a only; there is no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return JPGB_ERR_CUDA;
+    jpgb_encoder *e = new (std::nothrow) jpgb_encoder();
+    if (!e) return JPGB_ERR_NOMEM;
+    e->device = device;
+    if (cuda_stream) {
+        e->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete e;
+            return JPGB_ERR_CUDA;
+        }
+        e->own_stream = true;
+    }
+    for (int i = 0; i < JPGB_N_STAGES; ++i)
+        for (int k = 0; k < 2; ++k) cudaEventCreate(&e->ev[i][k]);
+    *out = e;
+    return JPGB_OK;
+}
+
+void jpgb_encoder_destroy(jpgb_encoder *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->bitpos, &e->seglen, &e->segpos,
+                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist};
+    for (DevBuf *b : bufs) b->release();
+    e->h_small.release();
+    e->h_hist.release();
+    e->h_tables.release();
+    for (int i = 0; i < JPGB_N_STAGES; ++i)
+        for (int k = 0; k < 2; ++k)
+            if (e->ev[i][k]) cudaEventDestroy(e->ev[i][k]);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char *jpgb_last_error(const jpgb_encoder *e) { return e ? e->err.c_str() : "no encoder"; }
+
+int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len, uint8_t **out, size_t *out_len) {
+    if (!out || !out_len) return JPGB_ERR_BAD_PARAMS;
+    *out = nullptr;
+    *out_len = 0;
+    const uint8_t *px[1] = {pixels};
+    return encode_host_batch(enc, p, px, len, 1, out, out_len);
+}
+
+void jpgb_free(void *buf) { std::free(buf); }
+
+int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len, jpgb_write_all_fn write_all,
+                        void *user) {
+    if (!write_all) return JPGB_ERR_BAD_PARAMS;
+    uint8_t *buf = nullptr;
+    size_t n = 0;
+    const int rc = jpgb_encode(enc, p, pixels, len, &buf, &n);
+    if (rc != JPGB_OK) return rc;
+    const int wrc = write_all(user, buf, n);
+    std::free(buf);
+    if (wrc != 0) return fail(enc, JPGB_ERR_SINK, "sink write_all failed");
+    return JPGB_OK;
+}
+
+int jpgb_encode_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels, size_t len_each, uint32_t n,
+                      uint8_t **outs, size_t *out_lens) {
+    return encode_host_batch(enc, p, pixels, len_each, n, outs, out_lens);
+}
+
+int jpgb_encode_batch_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels, size_t image_stride, uint32_t n,
+                             const void **d_files, uint64_t *offsets) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_pixels || !d_files || !offsets || n == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    Plan plan;
+    int rc = validate_and_plan(enc, p, image_stride, plan);
+    if (rc != JPGB_OK) return rc;
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    timing_begin(enc);
+    std::vector<uint64_t> off;
+    rc = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), image_stride, n, off);
+    if (rc != JPGB_OK) return rc;
+    timing_end(enc);
+    std::memcpy(offsets, off.data(), (size_t)(n + 1) * 8);
+    *d_files = enc->out.p;
+    return JPGB_OK;
+}
+
+int jpgb_coef_layout_for(const jpgb_params *p, jpgb_coef_layout *l) {
+    if (!p || !l) return JPGB_ERR_BAD_PARAMS;
+    Plan plan;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return rc;
+    std::memset(l, 0, sizeof(*l));
+    l->n_components = (uint32_t)plan.ncomp;
+    for (int c = 0; c < plan.ncomp; ++c) {
+        l->blocks_w[c] = plan.pad_w[c];
+        l->blocks_h[c] = plan.pad_h[c];
+        l->true_w[c] = plan.true_w[c];
+        l->true_h[c] = plan.true_h[c];
+        l->block_offset[c] = plan.block_off[c];
+    }
+    l->blocks_per_image = plan.blocks_per_image;
+    return JPGB_OK;
+}
+
+int jpgb_stage_a_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels, size_t image_stride, uint32_t n, void *d_coef) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_pixels || !d_coef || n == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    Plan plan;
+    const int rc = validate_and_plan(enc, p, image_stride, plan);
+    if (rc != JPGB_OK) return rc;
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    StageAParams ap;
+    plan.fill_stage_a(ap);
+    ap.pixels = static_cast<const uint8_t *>(d_pixels);
+    ap.coef = static_cast<int16_t *>(d_coef);
+    ap.image_stride = image_stride;
+    enc->launches = 0;
+    CK(launch_stage_a(ap, n, enc->stream), "stage A launch");
+    enc->launches = 1;
+    return JPGB_OK;
+}
+
+void jpgb_encoder_set_timing(jpgb_encoder *enc, int enabled) {
+    if (enc) enc->timing = enabled != 0;
+}
+int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]) {
+    if (!enc || !enc->have_timing) return JPGB_ERR_BAD_PARAMS;
+    std::memcpy(ms, enc->last_ms, sizeof(enc->last_ms));
+    return JPGB_OK;
+}
+uint32_t jpgb_encoder_last_launch_count(const jpgb_encoder *enc) { return enc ? enc->launches : 0; }
+
+const char *jpgb_version(void) { return "jpeg-encoder_b200 0.1 (sm_100a; parity target: jpeg-encoder 0.7.0)"; }
+
+} // extern "C"

@@ -1,0 +1,59 @@
+// Plain structs shared between the host planner and the kernels.
+#pragma once
+#include <cstdint>
+
+namespace jpgb {
+
+constexpr int kMaxScans = 256;  // 4 components x 64 progressive scans
+constexpr int kMaxSlots = 12;   // blocks per interleaved MCU: 8 (luma 2x4) + 2, or 3 + 8 for CMYK
+
+// Quantizer constants per table, natural order. q = (v*mul + (v < 0 ? add_neg : add_pos)) >> 16
+// reproduces `((abs(v) + corr) * recip) >> 15` with the sign re-applied (src/quantization.rs:291-307):
+// mul = 2*recip, add_pos = 2*corr*recip, add_neg = 2*(32767 - corr*recip).
+struct QuantConsts {
+    int32_t mul[64];
+    int32_t add_pos[64];
+    int32_t add_neg[64];
+};
+
+struct StageAParams {
+    const uint8_t *pixels;
+    int16_t *coef;
+    unsigned long long image_stride;     // bytes between images
+    unsigned long long blocks_per_image;
+    int width, height, bpp, color_type, ncomp;
+    int hmax, vmax;
+    int mcu_cols, mcu_rows;
+    int groups;            // 32-MCU groups per CTA tile
+    int tiles_per_row;
+    int tasks_per_group;   // warp tasks per group = sum over components of H_c*V_c
+    int tile_w_px, tile_h_px, tile_pitch; // pitch in bytes
+    // per warp task inside a group: component and block position inside the MCU
+    int8_t task_comp[kMaxSlots], task_v[kMaxSlots], task_h[kMaxSlots];
+    int comp_h[4], comp_v[4], comp_qt[4], comp_pw[4];
+    unsigned long long comp_off[4];
+    QuantConsts q[2];
+};
+
+struct DevScan {
+    int comp, ss, se;
+    unsigned n_units, bpu;
+    unsigned long long visit_base;
+    unsigned seg_base, n_segs;
+    unsigned sos_off, sos_len;  // into DevPlan::blob
+};
+
+struct DevPlan {
+    int n_scans, ncomp, n_slots, restart;   // restart interval in units (0 = off)
+    unsigned mcu_cols;
+    unsigned long long visits_per_image, blocks_per_image;
+    unsigned segs_per_image;
+    int8_t slot_comp[kMaxSlots], slot_v[kMaxSlots], slot_h[kMaxSlots];
+    int comp_h[4], comp_v[4], comp_tbl[4];
+    unsigned comp_pw[4], comp_tw[4];   // padded / true blocks per row
+    unsigned long long comp_off[4];
+    DevScan scans[kMaxScans];
+    unsigned char blob[kMaxScans * 10]; // SOS segments of scans 1.. (10 bytes each: single component)
+};
+
+} // namespace jpgb

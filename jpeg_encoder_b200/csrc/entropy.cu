@@ -1,0 +1,537 @@
+// Stage B: quantized coefficients -> JFIF bytes, entirely on the device.
+//
+// Replaces the reference's serial entropy coder and bit writer
+//   write_dc / write_ac_block / write_block / get_code      src/writer.rs:331-388, 455-470
+//   write_bits / flush / finalize_bit_buffer (0xFF stuffing) src/writer.rs:138-202
+//   the MCU / block walks with restart bookkeeping           src/encoder.rs:727-804, 823-861, 885-972
+//   optimize_huffman_table's symbol histogram                src/encoder.rs:1086-1200
+//
+// Vocabulary. A *visit* is one block coded in one scan (a block is visited once per scan that
+// touches it); visits are numbered in the reference's emission order. A *segment* is the run of
+// visits between two restart points of one scan (one segment per scan when restarts are off);
+// its bits start byte-aligned and end padded with 1-bits. The *unstuffed stream* is the complete
+// file before 0xFF stuffing: per image the header, then per segment its lead (RSTn marker or the
+// next scan's SOS) and its data bytes, then EOI. `raw_mask` flags header/marker bytes so that the
+// stuffing pass leaves their 0xFF alone.
+//
+//   symbol_size_kernel   visit -> number of bits                (DC differencing, run/size symbols)
+//   [exclusive scan]     bit position of every visit
+//   segment_len_kernel   segment -> lead + ceil(bits/8) + tail bytes
+//   [exclusive scan]     byte position of every segment in the unstuffed stream
+//   segment_lead_kernel  writes headers / RSTn / SOS / EOI, sets raw_mask
+//   emit_bits_kernel     visit -> code bits OR-ed into the unstuffed stream, pad bits at segment end
+//   count_ff_kernel      chunk -> number of data 0xFF bytes
+//   [exclusive scan]
+//   stuff_scatter_kernel copies every byte to its final place, inserting 0x00 after data 0xFF
+#include "kernels.h"
+
+namespace jpgb {
+namespace {
+
+struct VisitInfo {
+    const int16_t *blk;   // this block's 64 zig-zag coefficients
+    const int16_t *pred;  // block holding the DC predictor, or nullptr for "predictor is 0"
+    int comp, ss, se, tbl;
+    unsigned long long first_visit_of_seg; // within the image
+    unsigned seg_local;                    // segment index within the image
+    unsigned seg_in_scan;
+    int scan;
+    bool last_of_seg;
+};
+
+__device__ __forceinline__ int find_scan_by_visit(const DevPlan &P, unsigned long long v) {
+    int lo = 0, hi = P.n_scans - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.scans[mid].visit_base <= v) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int find_scan_by_seg(const DevPlan &P, unsigned s) {
+    int lo = 0, hi = P.n_scans - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.scans[mid].seg_base <= s) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Where does visit `v` (numbered within one image) live, and what precedes it?
+// Interleaved order: encoder.rs:747-791 (MCU raster; component, v, h inside the MCU).
+// Single-component order: encoder.rs:832 / 894 / 946 over encode_blocks' raster grid (:1030-1031).
+// Predictor reset at restart points: :753-756, :838, :900.
+__device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_t *coef_img, unsigned long long v) {
+    VisitInfo r;
+    const int k = find_scan_by_visit(P, v);
+    const DevScan &S = P.scans[k];
+    const unsigned long long rel = v - S.visit_base;
+    const unsigned unit = (unsigned)(rel / S.bpu), slot = (unsigned)(rel - (unsigned long long)unit * S.bpu);
+    const unsigned R = (unsigned)P.restart;
+    const bool restart_here = unit == 0 || (R && unit % R == 0);
+    unsigned long long blk, pred = 0;
+    bool has_pred = true;
+    int comp;
+    if (S.comp < 0) {
+        comp = P.slot_comp[slot];
+        const unsigned bv = P.slot_v[slot], bh = P.slot_h[slot];
+        const unsigned H = P.comp_h[comp], V = P.comp_v[comp], pw = P.comp_pw[comp];
+        const unsigned my = unit / P.mcu_cols, mx = unit - my * P.mcu_cols;
+        const unsigned long long off = P.comp_off[comp];
+        blk = off + (unsigned long long)(my * V + bv) * pw + mx * H + bh;
+        if (bh > 0) pred = blk - 1;
+        else if (bv > 0) pred = off + (unsigned long long)(my * V + bv - 1) * pw + mx * H + (H - 1);
+        else if (restart_here) has_pred = false;
+        else {
+            const unsigned pu = unit - 1, pmy = pu / P.mcu_cols, pmx = pu - pmy * P.mcu_cols;
+            pred = off + (unsigned long long)(pmy * V + V - 1) * pw + pmx * H + (H - 1);
+        }
+    } else {
+        comp = S.comp;
+        const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
+        const unsigned long long off = P.comp_off[comp];
+        const unsigned by = unit / tw, bx = unit - by * tw;
+        blk = off + (unsigned long long)by * pw + bx;
+        if (restart_here) has_pred = false;
+        else {
+            const unsigned pu = unit - 1, pby = pu / tw, pbx = pu - pby * tw;
+            pred = off + (unsigned long long)pby * pw + pbx;
+        }
+    }
+    r.blk = coef_img + blk * 64;
+    r.pred = has_pred ? coef_img + pred * 64 : nullptr;
+    r.comp = comp;
+    r.ss = S.ss;
+    r.se = S.se;
+    r.tbl = P.comp_tbl[comp];
+    r.scan = k;
+    r.seg_in_scan = R ? unit / R : 0;
+    r.seg_local = S.seg_base + r.seg_in_scan;
+    r.first_visit_of_seg = S.visit_base + (unsigned long long)r.seg_in_scan * R * S.bpu;
+    r.last_of_seg = slot == S.bpu - 1 && (unit == S.n_units - 1 || (R && (unit + 1) % R == 0));
+    return r;
+}
+
+// get_code, writer.rs:455-470: size = bit length of |v|, bits = low `size` bits of (v - (v<0))
+__device__ __forceinline__ void value_code(int v, int &size, uint32_t &bits) {
+    const int a = v < 0 ? -v : v;
+    size = 32 - __clz(a);
+    bits = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << size) - 1u);
+}
+
+// Bit sink. COUNT mode adds lengths; EMIT mode packs MSB-first into 32-bit big-endian words of the
+// unstuffed stream. The first and the last word of a visit are shared with its neighbours and are
+// merged with atomicOr (the stream is zero-initialised); interior words are owned and stored.
+template <bool EMIT>
+struct BitSink {
+    unsigned total = 0;
+    unsigned long long acc = 0;
+    int n = 0;
+    uint32_t *word = nullptr;
+    bool first = true;
+
+    __device__ __forceinline__ void begin(uint8_t *stream, unsigned long long bitpos) {
+        if (EMIT) {
+            word = reinterpret_cast<uint32_t *>(stream) + (bitpos >> 5);
+            n = (int)(bitpos & 31);
+        }
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        if (!EMIT) {
+            total += len;
+            return;
+        }
+        acc = (acc << len) | code;
+        n += len;
+        if (n >= 32) {
+            const uint32_t w = (uint32_t)(acc >> (n - 32));
+            const uint32_t be = __byte_perm(w, 0, 0x0123);
+            if (first) atomicOr(word, be);
+            else *word = be;
+            first = false;
+            ++word;
+            n -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (EMIT && n > 0) {
+            const uint32_t w = (uint32_t)(acc << (32 - n));
+            atomicOr(word, __byte_perm(w, 0, 0x0123));
+        }
+    }
+};
+
+// write_dc + write_ac_block restricted to [ss, se] for one visit (writer.rs:342-388).
+// A symbol without a code has lookup 0: only the value bits are written (release-build behaviour
+// of the reference).
+template <bool EMIT>
+__device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *__restrict__ dc_tab,
+                                           const uint32_t *__restrict__ ac_tab, BitSink<EMIT> &sink) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(vi.blk);
+    int run = 0;
+    const int first_ac = vi.ss == 0 ? 1 : vi.ss;
+    const int w_lo = vi.se == 0 ? 0 : first_ac >> 3, w_hi = vi.se >> 3;
+    if (vi.ss == 0) {
+        const int dc = vi.blk[0];
+        const int prev = vi.pred ? (int)vi.pred[0] : 0;
+        const int diff = (int)(int16_t)(dc - prev);
+        int size;
+        uint32_t bits;
+        value_code(diff, size, bits);
+        const uint32_t h = __ldg(dc_tab + size);
+        sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
+    }
+    if (vi.se == 0) return;
+    for (int w = w_lo; w <= w_hi; ++w) {
+        const uint4 q = __ldg(src + w);
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = w * 8 + j;
+            const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
+            if (k < first_ac || k > vi.se) continue;
+            if (c == 0) {
+                ++run;
+            } else {
+                if (run > 15) {
+                    const uint32_t z = __ldg(ac_tab + 0xF0);
+                    for (; run > 15; run -= 16) sink.put(z & 0xFFFFu, (int)(z >> 16));
+                }
+                int size;
+                uint32_t bits;
+                value_code(c, size, bits);
+                const uint32_t h = __ldg(ac_tab + ((run << 4) | size));
+                sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
+                run = 0;
+            }
+        }
+    }
+    if (run > 0) {
+        const uint32_t e = __ldg(ac_tab);
+        sink.put(e & 0xFFFFu, (int)(e >> 16));
+    }
+}
+
+__device__ __forceinline__ const uint32_t *huff_for(const EntropyBuffers &b, unsigned long long img, int tbl, int cls) {
+    return b.huff + (b.huff_per_image ? img * kHuffWordsPerImage : 0) + (size_t)(tbl * 2 + cls) * 256;
+}
+
+__global__ void __launch_bounds__(256) symbol_size_kernel(const EntropyBuffers b, unsigned long long n_visits) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_visits) return;
+    const DevPlan &P = *b.plan;
+    const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
+    const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
+    BitSink<false> sink;
+    code_visit<false>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    b.nbits[g] = sink.total;
+}
+
+// lead of local segment `s`: what the reference writes between the previous segment's last byte
+// and this segment's first: the file header (first segment of the image), the SOS of a later scan
+// (writer.rs:424-452) or RSTn (encoder.rs:748-752: marker index = restarts % 8).
+__device__ __forceinline__ unsigned lead_len(const EntropyBuffers &b, const DevPlan &P, unsigned long long img, int k,
+                                             unsigned seg_in_scan) {
+    if (seg_in_scan > 0) return 2;
+    if (k > 0) return P.scans[k].sos_len;
+    return b.hdr_len[b.huff_per_image ? img : 0];
+}
+
+__global__ void __launch_bounds__(256) segment_len_kernel(const EntropyBuffers b, unsigned long long n_segs) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_segs) return;
+    const DevPlan &P = *b.plan;
+    const unsigned long long img = g / P.segs_per_image;
+    const unsigned s = (unsigned)(g - img * P.segs_per_image);
+    const int k = find_scan_by_seg(P, s);
+    const DevScan &S = P.scans[k];
+    const unsigned i = s - S.seg_base;
+    const unsigned long long span = (unsigned long long)P.restart * S.bpu;
+    const unsigned long long vf = S.visit_base + i * span;
+    const unsigned long long vn = (i + 1 < S.n_segs) ? vf + span : S.visit_base + (unsigned long long)S.n_units * S.bpu;
+    const unsigned long long vb = img * P.visits_per_image;
+    const unsigned long long bits = b.bitpos[vb + vn] - b.bitpos[vb + vf];
+    const unsigned tail = s == P.segs_per_image - 1 ? 2u : 0u; // EOI, encoder.rs:564
+    b.seglen[g] = lead_len(b, P, img, k, i) + (unsigned)((bits + 7) >> 3) + tail;
+}
+
+__global__ void __launch_bounds__(256) zero_ustream_kernel(const EntropyBuffers b, unsigned long long n_segs_total) {
+    const unsigned long long bytes = b.segpos[n_segs_total];
+    const unsigned long long n16 = (bytes + 15) >> 4, nm = ((bytes + 31) >> 5);
+    uint4 *u = reinterpret_cast<uint4 *>(b.ustream);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        u[i] = make_uint4(0, 0, 0, 0);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += stride) b.raw_mask[i] = 0;
+}
+
+__device__ __forceinline__ void put_raw(const EntropyBuffers &b, unsigned long long pos, uint8_t byte) {
+    b.ustream[pos] = byte;
+    atomicOr(b.raw_mask + (pos >> 5), 1u << (pos & 31));
+}
+
+__global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers b, unsigned long long n_segs) {
+    // one warp per segment; lanes stride over the lead bytes (headers can be long: ICC, EXIF)
+    const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= n_segs) return;
+    const DevPlan &P = *b.plan;
+    const unsigned long long img = g / P.segs_per_image;
+    const unsigned s = (unsigned)(g - img * P.segs_per_image);
+    const int k = find_scan_by_seg(P, s);
+    const DevScan &S = P.scans[k];
+    const unsigned i = s - S.seg_base;
+    const unsigned long long pos = b.segpos[g];
+    if (i > 0) {
+        if (lane == 0) {
+            put_raw(b, pos, 0xFF);
+            put_raw(b, pos + 1, (uint8_t)(0xD0 + ((i - 1) & 7)));
+        }
+    } else if (k > 0) {
+        for (unsigned j = lane; j < S.sos_len; j += 32) put_raw(b, pos + j, P.blob[S.sos_off + j]);
+    } else {
+        const unsigned long long h = b.huff_per_image ? img : 0;
+        const unsigned n = b.hdr_len[h];
+        const uint8_t *src = b.hdr + h * b.hdr_stride;
+        for (unsigned j = lane; j < n; j += 32) put_raw(b, pos + j, src[j]);
+    }
+    if (s == P.segs_per_image - 1 && lane == 0) {
+        const unsigned long long end = b.segpos[g + 1];
+        put_raw(b, end - 2, 0xFF);
+        put_raw(b, end - 1, 0xD9);
+    }
+}
+
+__global__ void __launch_bounds__(256) emit_bits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_visits) return;
+    const DevPlan &P = *b.plan;
+    const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
+    const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
+    const unsigned long long seg = img * P.segs_per_image + vi.seg_local;
+    const unsigned long long data_byte = b.segpos[seg] + lead_len(b, P, img, vi.scan, vi.seg_in_scan);
+    const unsigned long long rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + vi.first_visit_of_seg];
+    const unsigned long long bitpos = data_byte * 8 + rel_bits;
+    BitSink<true> sink;
+    sink.begin(b.ustream, bitpos);
+    code_visit<true>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    if (vi.last_of_seg) { // finalize_bit_buffer, writer.rs:138-145: pad to the byte boundary with ones
+        const unsigned end_bits = (unsigned)((rel_bits + b.nbits[g]) & 7);
+        if (end_bits) sink.put((1u << (8 - end_bits)) - 1u, 8 - (int)end_bits);
+    }
+    sink.finish();
+}
+
+// ---- 0xFF stuffing (writer.rs:156-167) as count / scan / scatter ---------------------------------
+// A thread owns 16 consecutive bytes of the unstuffed stream and the 16 raw_mask bits beside them.
+__device__ __forceinline__ unsigned ff_bits16(const uint4 d, unsigned raw16, unsigned valid) {
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu) == 0xFFu) m |= 1u << i;
+    m &= ~raw16;
+    if (valid < 16) m &= (1u << valid) - 1u;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b, unsigned long long bytes) {
+    __shared__ unsigned warp_sums[8];
+    const unsigned long long base = (unsigned long long)blockIdx.x * kStuffChunk + (unsigned long long)threadIdx.x * 16;
+    unsigned cnt = 0;
+    if (base < bytes) {
+        const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + base);
+        const unsigned raw = (b.raw_mask[base >> 5] >> (base & 31)) & 0xFFFFu;
+        const unsigned valid = bytes - base < 16 ? (unsigned)(bytes - base) : 16u;
+        cnt = __popc(ff_bits16(d, raw, valid));
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < 8; ++i) t += warp_sums[i];
+        b.ffcount[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers b, unsigned long long bytes) {
+    __shared__ unsigned warp_excl[9];
+    const unsigned long long base = (unsigned long long)blockIdx.x * kStuffChunk + (unsigned long long)threadIdx.x * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 d = make_uint4(0, 0, 0, 0);
+    unsigned m = 0, valid = 0;
+    if (base < bytes) {
+        d = *reinterpret_cast<const uint4 *>(b.ustream + base);
+        const unsigned raw = (b.raw_mask[base >> 5] >> (base & 31)) & 0xFFFFu;
+        valid = bytes - base < 16 ? (unsigned)(bytes - base) : 16u;
+        m = ff_bits16(d, raw, valid);
+    }
+    const unsigned cnt = __popc(m);
+    unsigned inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_excl[warp + 1] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        warp_excl[0] = 0;
+        for (int i = 1; i <= 8; ++i) warp_excl[i] += warp_excl[i - 1];
+    }
+    __syncthreads();
+    if (valid == 0) return;
+    unsigned long long o = base + b.ffpos[blockIdx.x] + warp_excl[warp] + (inc - cnt);
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if ((unsigned)i < valid) {
+            b.out[o++] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+            if (m & (1u << i)) b.out[o++] = 0x00;
+        }
+    }
+}
+
+// byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
+// bytes that precede it
+__global__ void file_offsets_kernel(const EntropyBuffers b, unsigned n_images, unsigned long long bytes) {
+    const unsigned img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img > n_images) return;
+    const DevPlan &P = *b.plan;
+    const unsigned long long pos = img == n_images ? bytes : b.segpos[(unsigned long long)img * P.segs_per_image];
+    const unsigned long long chunk = pos / kStuffChunk;
+    unsigned long long ff = pos == bytes && chunk * kStuffChunk == pos ? b.ffpos[chunk] : b.ffpos[chunk];
+    for (unsigned long long i = chunk * kStuffChunk; i < pos; ++i)
+        if (b.ustream[i] == 0xFF && !((b.raw_mask[i >> 5] >> (i & 31)) & 1u)) ++ff;
+    b.file_off[img] = pos + ff;
+}
+
+// ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
+// One thread per block of each component's *true* grid. DC category of the chained difference with
+// no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL
+// for runs > 15, EOB when a band ends in zeros. Bins: [image][table][dc|ac][257].
+__global__ void __launch_bounds__(256) histogram_kernel(const DevPlan *plan, const int16_t *coef, unsigned long long n_blocks_total,
+                                                        unsigned long long blocks_true_per_image, uint32_t *hist,
+                                                        int bands, int per_band) {
+    __shared__ unsigned sh[2 * 2 * 257];
+    for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const DevPlan &P = *plan;
+    const unsigned long long g0 = (unsigned long long)blockIdx.x * blockDim.x;
+    const unsigned long long g = g0 + threadIdx.x;
+    const unsigned long long img_cta = g0 / blocks_true_per_image; // CTAs never straddle images (grid is per image)
+    if (g < n_blocks_total) {
+        unsigned long long r = g - img_cta * blocks_true_per_image;
+        int comp = 0;
+        for (; comp < P.ncomp - 1; ++comp) {
+            const unsigned long long nb = (unsigned long long)P.comp_tw[comp] * (P.scans[comp].n_units / P.comp_tw[comp]);
+            if (r < nb) break;
+            r -= nb;
+        }
+        const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
+        const unsigned by = (unsigned)(r / tw), bx = (unsigned)(r - (unsigned long long)by * tw);
+        const int16_t *img_coef = coef + img_cta * P.blocks_per_image * 64;
+        const int16_t *blk = img_coef + (P.comp_off[comp] + (unsigned long long)by * pw + bx) * 64;
+        int prev = 0;
+        if (r > 0) {
+            const unsigned long long pr = r - 1;
+            const unsigned pby = (unsigned)(pr / tw), pbx = (unsigned)(pr - (unsigned long long)pby * tw);
+            prev = img_coef[(P.comp_off[comp] + (unsigned long long)pby * pw + pbx) * 64];
+        }
+        unsigned *h = sh + P.comp_tbl[comp] * 2 * 257;
+        const int diff = (int)(int16_t)(blk[0] - prev);
+        atomicAdd(h + (32 - __clz(diff < 0 ? -diff : diff)), 1u);
+        unsigned *ha = h + 257;
+        const uint4 *src = reinterpret_cast<const uint4 *>(blk);
+        int run = 0, band = 0, band_end = bands == 1 ? 64 : per_band; // band b covers [max(b*per,1), (b+1)*per), last to 64
+        for (int w = 0; w < 8; ++w) {
+            const uint4 q = __ldg(src + w);
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = w * 8 + j;
+                if (k == 0) continue;
+                if (k == band_end) { // band boundary: close the previous band
+                    if (run > 0) atomicAdd(ha, 1u);
+                    run = 0;
+                    ++band;
+                    band_end = band == bands - 1 ? 64 : (band + 1) * per_band;
+                }
+                const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
+                if (c == 0) {
+                    ++run;
+                } else {
+                    for (; run > 15; run -= 16) atomicAdd(ha + 0xF0, 1u);
+                    atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
+                    run = 0;
+                }
+            }
+        }
+        if (run > 0) atomicAdd(ha, 1u);
+    }
+    __syncthreads();
+    uint32_t *dst = hist + img_cta * (2 * 2 * 257);
+    for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x)
+        if (sh[i]) atomicAdd(dst + i, sh[i]);
+}
+
+} // namespace
+
+static inline unsigned grid_for(unsigned long long n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hp, const int16_t *coef, uint32_t n_images, uint32_t *hist,
+                             cudaStream_t stream) {
+    // sequential / progressive plans only: scans 0..ncomp-1 are one per component over its true grid
+    unsigned long long per_image = 0;
+    for (int c = 0; c < hp.ncomp; ++c) per_image += hp.scans[c].n_units;
+    const int bands = hp.n_scans > hp.ncomp ? hp.n_scans / hp.ncomp - 1 : 1;
+    const int per_band = bands > 1 ? 64 / bands : 64;
+    const unsigned ctas_per_image = grid_for(per_image, 256);
+    // one launch per image keeps CTAs from straddling images; images in a batch are few in optimized mode
+    for (uint32_t i = 0; i < n_images; ++i) {
+        histogram_kernel<<<ctas_per_image, 256, 0, stream>>>(plan, coef + (size_t)i * hp.blocks_per_image * 64, per_image, per_image,
+                                                            hist + (size_t)i * (2 * 2 * 257), bands, per_band);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    const unsigned long long nv = hp.visits_per_image * n;
+    symbol_size_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+    return cudaGetLastError();
+}
+cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    const unsigned long long ns = (unsigned long long)hp.segs_per_image * n;
+    segment_len_kernel<<<grid_for(ns, 256), 256, 0, s>>>(b, ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t s) {
+    zero_ustream_kernel<<<148 * 8, 256, 0, s>>>(b, n_segs_total);
+    return cudaGetLastError();
+}
+cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    const unsigned long long ns = (unsigned long long)hp.segs_per_image * n;
+    segment_lead_kernel<<<grid_for(ns * 32, 128), 128, 0, s>>>(b, ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    const unsigned long long nv = hp.visits_per_image * n;
+    emit_bits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {
+    count_ff_kernel<<<grid_for(bytes, kStuffChunk), 256, 0, s>>>(b, bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {
+    stuff_scatter_kernel<<<grid_for(bytes, kStuffChunk), 256, 0, s>>>(b, bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, uint64_t bytes, cudaStream_t s) {
+    file_offsets_kernel<<<grid_for(n + 1ull, 128), 128, 0, s>>>(b, n, bytes);
+    return cudaGetLastError();
+}
+
+} // namespace jpgb

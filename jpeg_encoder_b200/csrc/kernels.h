@@ -1,0 +1,61 @@
+// Launchers of the CUDA kernels (sm_100a). All work is queued on `stream`; nothing here syncs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/jpegenc_b200.h"
+#include "device_types.h"
+
+namespace jpgb {
+
+// stage_a.cu -- colour + decimate + level shift + fDCT + quantize -> zig-zag i16 coefficients
+cudaError_t launch_stage_a(const StageAParams &p, uint32_t n_images, cudaStream_t stream);
+
+// Huffman code tables as the kernels see them: [image][table 0|1][class dc|ac][256] of (size<<16)|code
+constexpr size_t kHuffWordsPerImage = 2 * 2 * 256;
+
+// Buffers of one encode call (all device pointers). Sizes are in the comments; `n` = images.
+struct EntropyBuffers {
+    const DevPlan *plan;           // device copy of the plan
+    const int16_t *coef;           // n * blocks_per_image * 64
+    const uint32_t *huff;          // n_huff * kHuffWordsPerImage; n_huff is 1 (shared) or n (optimized)
+    int huff_per_image;            // 0: all images share tables[0]; 1: one set per image
+    uint32_t *nbits;               // n * visits_per_image
+    unsigned long long *bitpos;    // n * visits_per_image + 1   (exclusive scan of nbits)
+    uint32_t *seglen;              // n * segs_per_image          (lead + data + tail bytes of a segment)
+    unsigned long long *segpos;    // n * segs_per_image + 1      (exclusive scan of seglen)
+    const uint32_t *hdr_len;       // n_huff entries: bytes of file header (SOI .. first SOS)
+    const uint8_t *hdr;            // n_huff * hdr_stride bytes
+    uint32_t hdr_stride;
+    uint8_t *ustream;              // unstuffed stream incl. headers/markers, zero-initialised
+    uint32_t *raw_mask;            // 1 bit per ustream byte: header/marker byte, exempt from stuffing
+    uint32_t *ffcount;             // per chunk of kStuffChunk bytes
+    unsigned long long *ffpos;     // exclusive scan of ffcount (+1)
+    uint8_t *out;                  // final files back to back
+    unsigned long long *file_off;  // n + 1 offsets into `out`
+    void *scan_tmp;                // scratch for the scans
+    size_t scan_tmp_bytes;
+};
+
+constexpr int kStuffChunk = 4096; // bytes of unstuffed stream per CTA in the stuffing kernels
+
+// entropy.cu
+cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hplan, const int16_t *coef, uint32_t n_images,
+                             uint32_t *hist /* n * 2 tables * 2 classes * 257 */, cudaStream_t stream);
+cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t stream);
+cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
+cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, uint64_t ustream_bytes,
+                                cudaStream_t stream);
+
+// scan.cu -- device-wide exclusive prefix sum of u32 into u64; out has n + 1 entries (out[n] = total)
+size_t scan_tmp_bytes(uint64_t n);
+cudaError_t launch_exclusive_scan(const uint32_t *in, unsigned long long *out, uint64_t n, void *tmp, cudaStream_t stream,
+                                  uint32_t *launches);
+
+} // namespace jpgb

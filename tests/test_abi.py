@@ -1,0 +1,108 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/jpegenc_b200.h
+declares; host-side planning (no kernels) agrees with the oracle's geometry; the Python mirror
+behaves like the reference's Encoder setters. No compute calls -- there is no GPU here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as entry
+import jpeg_encoder_b200 as je
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_and_exported_symbols():
+    lib_path = entry.build()
+    assert os.path.exists(lib_path)
+    header = open(os.path.join(ROOT, "include", "jpegenc_b200.h")).read()
+    declared = set(re.findall(r"\b(jpgb_[a-z_0-9]+)\s*\(", header))
+    declared -= {"jpgb_write_all_fn"}
+    assert len(declared) >= 14
+    lib = C.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export %s" % name
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(ROOT, "jpeg_encoder_b200", "libjpegenc_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(je.EncodingError) as e:
+        je.Encoder(90).encode(bytes(12), 2, 2, je.ColorType.Rgb)
+    assert e.value.kind == "Cuda"
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jpeg_encoder_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower().replace("# the oracle", ""), "%s mentions the oracle" % f
+
+
+def test_params_default_matches_encoder_new():
+    lib = je.load_library()
+    from jpeg_encoder_b200.encoder import _Params
+    for q, samp in ((89, 0x22), (90, 0x11), (100, 0x11), (1, 0x22)):
+        p = _Params()
+        lib.jpgb_params_default(C.byref(p), q)
+        assert (p.quality, p.sampling) == (q, samp)
+        assert (p.density_unit, p.density_x, p.density_y) == (0, 1, 1)
+        assert p.progressive_scans == 0 and p.restart_interval == 0 and p.optimize_huffman == 0
+        assert je.Encoder(q).sampling_factor().get_sampling_factors() == ((samp >> 4), samp & 15)
+
+
+def test_coef_layout_matches_reference_block_counts():
+    """SURVEY.md 8a block counts: C1 32640+8160+8160, C2 512^2+2*256^2 (src/encoder.rs:713-717, 1012-1025)."""
+    e = je.Encoder(90)
+    e.set_sampling_factor(je.SamplingFactor.F_2_2)
+    lay = e.coef_layout(1920, 1080, je.ColorType.Rgb)
+    assert [lay.blocks_w[c] * lay.blocks_h[c] for c in range(3)] == [32640, 8160, 8160]
+    assert lay.blocks_per_image == 48960
+    assert (lay.true_w[0], lay.true_h[0], lay.true_w[1], lay.true_h[1]) == (240, 135, 120, 68)
+    lay = e.coef_layout(4096, 4096, je.ColorType.Rgb)
+    assert lay.blocks_per_image == 512 * 512 + 2 * 256 * 256
+    e.set_sampling_factor(je.SamplingFactor.F_4_1)
+    lay = e.coef_layout(258, 128, je.ColorType.Rgb)  # 9 MCU columns of 32 px
+    assert (lay.blocks_w[0], lay.blocks_h[0], lay.true_w[0], lay.true_w[1]) == (36, 16, 33, 9)
+    lay = je.Encoder(95).coef_layout(8192, 8192, je.ColorType.CmykAsYcck)
+    assert lay.n_components == 4 and lay.blocks_per_image == 4 * 1024 * 1024
+
+
+def test_setters_mirror_reference():
+    e = je.Encoder(100)
+    e.set_progressive(True)
+    assert e.progressive_scans() == 4  # src/encoder.rs:1323-1331
+    e.set_progressive(False)
+    assert e.progressive_scans() is None
+    with pytest.raises(ValueError):
+        e.set_progressive_scans(1)
+    with pytest.raises(ValueError):
+        e.set_progressive_scans(65)
+    e.set_restart_interval(0)
+    assert e.restart_interval() is None
+    with pytest.raises(je.EncodingError) as err:
+        e.add_app_segment(0, b"x")
+    assert err.value.kind == "InvalidAppSegment"
+    with pytest.raises(je.EncodingError) as err:
+        e.add_app_segment(1, bytes(65534))
+    assert err.value.kind == "AppSegmentTooLarge"
+    with pytest.raises(je.EncodingError) as err:
+        e.add_icc_profile(bytes(255 * 65519))
+    assert err.value.kind == "IccTooLarge"
+    assert je.PixelDensity.dpi(300) == je.PixelDensity((300, 300), je.PixelDensityUnit.Inches)
+    for f in je.SamplingFactor:  # src/encoder.rs:1302-1321
+        h, v = f.get_sampling_factors()
+        assert je.SamplingFactor.from_factors(h, v).get_sampling_factors() == (h, v)
+    assert je.SamplingFactor.R_4_2_0.get_sampling_factors() == (2, 2)
+    assert je.SamplingFactor.from_factors(4, 4) is None

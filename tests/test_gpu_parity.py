@@ -1,0 +1,240 @@
+"""Parity tests proper: the CUDA path through the C ABI against the CPU oracle, byte for byte."""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import images
+from cases import BPP, CT, gpu_encode, make_encoder, oracle_encode
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _img(color, w, h, seed=1):
+    ch = BPP[color]
+    return images.photo_like(w, h, ch, seed=seed)
+
+
+def _same(color, w, h, cfg, img=None, seed=1):
+    img = _img(color, w, h, seed) if img is None else img
+    got = gpu_encode(img, w, h, color, cfg)
+    want = oracle_encode(img, w, h, color, cfg)
+    if got != want:
+        n = min(len(got), len(want))
+        first = next((i for i in range(n) if got[i] != want[i]), n)
+        pytest.fail("bytes differ for %s %dx%d %r: len %d vs %d, first diff at %d" % (color, w, h, cfg, len(got), len(want), first))
+    return got
+
+
+# ---- stage A on its own: coefficients bit-exact --------------------------------------------------
+@pytest.mark.parametrize("color,sampling", [("rgb", (2, 2)), ("rgb", (1, 1)), ("rgb", (4, 1)), ("rgb", (2, 4)), ("luma", (1, 1)),
+                                            ("cmyk_as_ycck", (1, 1)), ("cmyk", (2, 2)), ("bgra", (2, 1)), ("ycck", (1, 2))])
+def test_stage_a_coefficients(color, sampling):
+    import torch
+    import jpeg_encoder_b200 as je
+    w, h = 203, 131
+    img = _img(color, w, h)
+    cfg = dict(quality=85, sampling=sampling)
+    enc = make_encoder(cfg)
+    lay = enc.coef_layout(w, h, CT[color][1])
+    d_px = torch.from_numpy(img.reshape(-1).copy()).cuda()
+    d_coef = torch.full((lay.blocks_per_image * 64,), 12345, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    enc.stage_a_device(d_px.data_ptr(), d_px.numel(), 1, d_coef.data_ptr(), w, h, CT[color][1])
+    je.default_device(0)  # same context
+    import ctypes
+    # the context runs on its own stream: synchronise the device before reading
+    torch.cuda.synchronize()
+    got = d_coef.cpu().numpy().reshape(-1, 64)
+    want = orc.coefficients(img, w, h, CT[color][0], **cfg)
+    for c in range(lay.n_components):
+        o, n = lay.block_offset[c], lay.blocks_w[c] * lay.blocks_h[c]
+        assert n == want[c].shape[0]
+        np.testing.assert_array_equal(got[o:o + n], want[c], err_msg="component %d" % c)
+
+
+# ---- the reference's own end-to-end cases (src/lib.rs:188-553), now compared on bytes -----------
+REF_RGB_CASES = {
+    "rgb_100": dict(quality=100),
+    "rgb_80": dict(quality=80),
+    "custom_q_table": dict(quality=100, qtables=([1] * 64, [1] * 64)),
+    "2_2": dict(quality=100, sampling=(2, 2)),
+    "2_1": dict(quality=100, sampling=(2, 1)),
+    "4_1": dict(quality=100, sampling=(4, 1)),
+    "1_1": dict(quality=100, sampling=(1, 1)),
+    "1_4": dict(quality=100, sampling=(1, 4)),
+    "progressive": dict(quality=100, sampling=(2, 1), progressive_scans=4),
+    "optimized": dict(quality=100, sampling=(2, 2), optimize_huffman=True),
+    "optimized_progressive": dict(quality=100, sampling=(2, 1), progressive_scans=4, optimize_huffman=True),
+    "restart": dict(quality=100, restart_interval=32),
+    "restart_4_1": dict(quality=100, sampling=(4, 1), restart_interval=32),
+    "restart_progressive": dict(quality=85, progressive_scans=4, restart_interval=32),
+    "app_segment": dict(quality=100, app_segments=[(15, b"HOHOHO\0")]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(REF_RGB_CASES))
+def test_reference_rgb_cases(name):
+    jpg = _same("rgb", 258, 128, REF_RGB_CASES[name], img=images.ref_img_rgb())
+    im = Image.open(io.BytesIO(jpg))
+    im.load()
+    assert im.size == (258, 128)
+    assert np.abs(np.asarray(im).astype(int) - images.ref_img_rgb().astype(int)).max() < 20  # src/lib.rs:176-185
+
+
+def test_reference_other_color_cases():
+    _same("luma", 258, 128, dict(quality=100), img=images.ref_img_gray())
+    _same("rgba", 258, 128, dict(quality=80), img=images.ref_img_rgba())
+    _same("cmyk", 258, 192, dict(quality=100), img=images.ref_img_cmyk())
+    _same("cmyk_as_ycck", 258, 192, dict(quality=100), img=images.ref_img_cmyk())
+    data = np.array([[[0xFB, 0x15, 0x15]]], np.uint8)  # src/lib.rs:541-553
+    _same("rgb", 1, 1, dict(quality=100, sampling=(2, 2), optimize_huffman=True), img=data)
+
+
+def test_icc_profile():
+    import jpeg_encoder_b200 as je
+    icc = bytes(i % 255 for i in range(128 * 1024))
+    enc = je.Encoder(100)
+    enc.add_icc_profile(icc)
+    img = images.ref_img_rgb()
+    jpg = enc.encode(img, 258, 128, je.ColorType.Rgb)
+    maxc = 65535 - 2 - 12 - 2
+    chunks = [icc[i:i + maxc] for i in range(0, len(icc), maxc)]
+    segs = [(2, b"ICC_PROFILE\0" + bytes([i + 1, len(chunks)]) + c) for i, c in enumerate(chunks)]
+    assert jpg == orc.encode(img, 258, 128, orc.RGB, quality=100, app_segments=segs)
+    assert Image.open(io.BytesIO(jpg)).info.get("icc_profile") == icc
+
+
+# ---- the wider matrix ----------------------------------------------------------------------------
+@pytest.mark.parametrize("color", sorted(CT))
+@pytest.mark.parametrize("mode", ["baseline", "optimized", "progressive", "restart7", "opt_prog_restart"])
+def test_color_types_by_mode(color, mode):
+    cfg = dict(quality=77, sampling=(2, 2))
+    if mode == "optimized":
+        cfg["optimize_huffman"] = True
+    elif mode == "progressive":
+        cfg["progressive_scans"] = 4
+    elif mode == "restart7":
+        cfg["restart_interval"] = 7
+    elif mode == "opt_prog_restart":
+        cfg.update(optimize_huffman=True, progressive_scans=6, restart_interval=5)
+    _same(color, 150, 91, cfg, seed=hash((color, mode)) % 1000)
+
+
+@pytest.mark.parametrize("sampling", [(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (4, 2), (1, 4), (2, 4)])
+@pytest.mark.parametrize("color", ["rgb", "cmyk", "ycck"])
+def test_sampling_factors(color, sampling):
+    for extra in (dict(), dict(restart_interval=3), dict(progressive_scans=3, restart_interval=11)):
+        _same(color, 97, 75, dict(quality=60, sampling=sampling, **extra))
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 3), (8, 8), (9, 17), (16, 16), (17, 1), (1, 33), (255, 2), (513, 31), (640, 480)])
+def test_ragged_sizes(w, h):
+    for cfg in (dict(quality=90, sampling=(2, 2)), dict(quality=50, sampling=(1, 1), optimize_huffman=True),
+                dict(quality=95, sampling=(4, 2), progressive_scans=2)):
+        _same("rgb", w, h, cfg, seed=w * 1000 + h)
+        _same("luma", w, h, cfg, seed=w * 1000 + h + 1)
+
+
+@pytest.mark.parametrize("kind", range(9))
+def test_preset_quantization_tables(kind):
+    _same("rgb", 120, 80, dict(quality=70, qtables=(kind, (kind + 3) % 9)))
+
+
+def test_custom_tables_including_truncated_dqt():
+    rng = np.random.default_rng(5)
+    t1 = rng.integers(1, 256, 64).tolist()
+    t2 = rng.integers(1, 3000, 64).tolist()  # > 255: DQT byte is truncated, quantizer uses the full value (Q10)
+    t2[0] = 0  # clamped to 1
+    _same("rgb", 160, 120, dict(quality=33, qtables=(t1, t2), sampling=(2, 1)))
+    _same("cmyk_as_ycck", 64, 48, dict(quality=95, qtables=(t1, t1), sampling=(1, 1)))
+
+
+@pytest.mark.parametrize("q", [1, 10, 49, 50, 51, 89, 90, 100])
+def test_quality_sweep_default_sampling(q):
+    _same("rgb", 100, 60, dict(quality=q, sampling=None))
+
+
+@pytest.mark.parametrize("scans", [2, 3, 4, 5, 16, 33, 34, 63, 64])
+def test_progressive_scan_counts(scans):
+    _same("rgb", 64, 40, dict(quality=80, sampling=(2, 2), progressive_scans=scans))
+    _same("ycck", 40, 24, dict(quality=100, sampling=(1, 1), progressive_scans=scans, restart_interval=2))
+
+
+@pytest.mark.parametrize("ri", [1, 2, 8, 9, 64, 1000, 65535])
+def test_restart_intervals(ri):
+    _same("rgb", 200, 120, dict(quality=85, sampling=(2, 2), restart_interval=ri))
+    _same("rgb", 200, 120, dict(quality=85, sampling=(2, 2), restart_interval=ri, optimize_huffman=True))  # Q18
+
+
+def test_noise_and_extremes():
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 256, (96, 136, 3), dtype=np.uint8)
+    for cfg in (dict(quality=100, sampling=(1, 1)), dict(quality=100, sampling=(2, 2), optimize_huffman=True),
+                dict(quality=100, qtables=([1] * 64, [1] * 64), progressive_scans=4)):
+        _same("rgb", 136, 96, cfg, img=noise)
+    for v in (0, 255):
+        _same("rgb", 40, 40, dict(quality=90, sampling=(2, 2)), img=np.full((40, 40, 3), v, np.uint8))
+    cb = ((np.indices((64, 64)).sum(axis=0) % 2) * 255).astype(np.uint8)
+    _same("luma", 64, 64, dict(quality=100), img=cb)
+    _same("rgb", 64, 64, dict(quality=100, sampling=(1, 1)), img=np.stack([cb, 255 - cb, cb], -1))
+    ff = images.bench_img(320, 200)  # many 0xFF bytes in the entropy stream
+    _same("rgb", 320, 200, dict(quality=100, sampling=(1, 1)), img=ff)
+
+
+def test_density_and_trailing_bytes():
+    _same("rgb", 33, 21, dict(quality=90, density=(1, 300, 300)))
+    _same("rgb", 33, 21, dict(quality=90, density=(2, 118, 59)))
+    img = _img("rgb", 33, 21)
+    extra = np.concatenate([img.reshape(-1), np.arange(77, dtype=np.uint8)])
+    assert gpu_encode(extra, 33, 21, "rgb", dict(quality=90)) == oracle_encode(img, 33, 21, "rgb", dict(quality=90))
+
+
+def test_errors_mirror_reference():
+    import jpeg_encoder_b200 as je
+    with pytest.raises(je.EncodingError) as e:
+        je.Encoder(90).encode(np.zeros(10, np.uint8), 4, 4, je.ColorType.Rgb)
+    assert e.value.kind == "BadImageData"
+    with pytest.raises(je.EncodingError) as e:
+        je.Encoder(90).encode(np.zeros(10, np.uint8), 0, 4, je.ColorType.Rgb)
+    assert e.value.kind == "ZeroImageDimensions"
+
+
+def test_sink_and_batch():
+    import jpeg_encoder_b200 as je
+    img = _img("rgb", 120, 72)
+    cfg = dict(quality=88, sampling=(2, 2))
+    buf = io.BytesIO()
+    make_encoder(cfg).encode_to(buf, img, 120, 72, je.ColorType.Rgb)
+    assert buf.getvalue() == oracle_encode(img, 120, 72, "rgb", cfg)
+    imgs = [_img("rgb", 120, 72, seed=s) for s in range(7)]
+    for c in (cfg, dict(quality=70, sampling=(2, 2), optimize_huffman=True, restart_interval=9), dict(quality=70, progressive_scans=4)):
+        outs = make_encoder(c).encode_batch(imgs, 120, 72, je.ColorType.Rgb)
+        assert len(outs) == 7
+        for im, o in zip(imgs, outs):
+            assert o == oracle_encode(im, 120, 72, "rgb", c)
+
+
+# ---- BASELINE.json configurations at full size (oracle finishes in seconds up to C2) -------------
+def test_config1_1080p_baseline():
+    _same("rgb", 1920, 1080, dict(quality=90, sampling=(2, 2)), img=images.bench_img(1920, 1080))
+    _same("rgb", 1920, 1080, dict(quality=90, sampling=(2, 2)), img=images.photo_like(1920, 1080, 3))
+
+
+def test_config2_4096_optimized_restart64():
+    _same("rgb", 4096, 4096, dict(quality=85, sampling=(2, 2), optimize_huffman=True, restart_interval=64),
+          img=images.photo_like(4096, 4096, 3, seed=2))
+
+
+def test_config4_small_scale_gray_and_ycck_custom_tables():
+    rng = np.random.default_rng(4)
+    t = rng.integers(1, 64, 64).tolist()
+    _same("luma", 2048, 1024, dict(quality=95, sampling=(1, 1), qtables=(t, t)), img=images.photo_like(2048, 1024, 1))
+    _same("cmyk_as_ycck", 1024, 768, dict(quality=95, sampling=(1, 1), qtables=(t, t)), img=images.photo_like(1024, 768, 4))
+
+
+def test_config5_progressive_420_medium():
+    _same("rgb", 2048, 2048, dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048),
+          img=images.photo_like(2048, 2048, 3, seed=6))
