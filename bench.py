@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the JPEG encode hot path on N B200s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4a|c4b] [--impl reference]
+
+A step = one pass of the whole encode path (colour -> DCT -> quant -> entropy -> stuffed JFIF bytes)
+over one batch of synthetic frames. Default workload: BASELINE config 3, a batch of 1920x1080 RGB
+frames, q=90, 4:2:0, standard Huffman tables, sharded by image (each rank owns `--batch` frames: weak
+scaling, no data-path collective). `value` is measured with inputs resident in HBM; `e2e` goes
+through the host-buffer C ABI (pinned host pixels in, host JPEG bytes out, copies inside the timed
+region). `roofline` is the colour+DCT+quant kernel against the measured HBM peak. `cpu_baseline`
+is the CPU restatement of the reference (oracle/) on the host cores: a reported baseline, not the
+target. `--impl reference` times only that CPU restatement (the Rust crate cannot be built here:
+no Rust toolchain in the image).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (width, height, color, cfg, default batch per GPU, description)
+    "c1": (1920, 1080, "rgb", dict(quality=90, sampling=(2, 2)), 1, "1 x 1920x1080 RGB q90 4:2:0 baseline (BASELINE config 1)"),
+    "c2": (4096, 4096, "rgb", dict(quality=85, sampling=(2, 2), optimize_huffman=True, restart_interval=64), 1,
+           "1 x 4096x4096 RGB q85 4:2:0 optimized Huffman, restart 64 (BASELINE config 2)"),
+    "c3": (1920, 1080, "rgb", dict(quality=90, sampling=(2, 2)), 1024,
+           "batch of 1920x1080 RGB q90 4:2:0 baseline frames, sharded by image (BASELINE config 3)"),
+    "c4a": (8192, 8192, "luma", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
+            "1 x 8192x8192 grayscale q95 custom tables (BASELINE config 4a)"),
+    "c4b": (8192, 8192, "cmyk_as_ycck", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
+            "1 x 8192x8192 CMYK->YCCK q95 4:4:4 custom tables (BASELINE config 4b)"),
+}
+BPP = {"luma": 1, "rgb": 3, "cmyk_as_ycck": 4}
+DISTINCT = 16  # distinct synthetic frames; the batch repeats them (inputs stay >> L2: 6.2 MB per frame)
+
+
+def custom_table():
+    """fixed non-preset table, all values 1..255 so the file still decodes"""
+    return [min(255, 2 + ((i % 8) + (i // 8)) * 3 + (i * 7) % 5) for i in range(64)]
+
+
+def resolve_cfg(cfg):
+    cfg = dict(cfg)
+    if cfg.get("qtables") == "custom":
+        t = custom_table()
+        cfg["qtables"] = (t, t)
+    return cfg
+
+
+def frames_for(width, height, color, n_distinct):
+    import images
+    return [images.synth_frame(width, height, BPP[color], seed=s) for s in range(n_distinct)]
+
+
+def stage_a_bytes(width, height, color, cfg):
+    """Algorithmic bytes of the colour+DCT+quant kernel per image: w*h*bpp read + 128 B per block written
+    (block counts as src/encoder.rs:713-717)."""
+    import jpeg_encoder_b200 as je
+    from cases import CT, make_encoder
+    lay = make_encoder(cfg).coef_layout(width, height, CT[color][1])
+    return width * height * BPP[color] + 128 * int(lay.blocks_per_image)
+
+
+# ---- CPU baseline (oracle) ------------------------------------------------------------------------
+def cpu_encode_rate(frames, width, height, color, cfg, seconds, threads):
+    """One encode per thread on `threads` host threads for about `seconds`; returns (MP/s, frames done)."""
+    from cases import CT
+    from oracle import oracle as orc
+    orc.lib(native=True)  # built with -march=native on the machine that times it
+    ct = CT[color][0]
+    done = [0] * threads
+    stop = time.perf_counter() + seconds
+
+    def work(i):
+        k = i
+        while True:
+            orc.encode(frames[k % len(frames)], width, height, ct, native=True, **cfg)
+            done[i] += 1
+            k += threads
+            if time.perf_counter() >= stop:
+                break
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    return n * width * height / 1e6 / dt, n
+
+
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = self.proc.communicate()[0]
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm_sorted = sorted(sm)
+        # median of the samples taken under load = upper half of the distribution
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the product arm ------------------------------------------------------------------------------
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    import jpeg_encoder_b200 as je
+    from cases import CT, make_encoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev_t = torch.device("cuda", local)
+
+    width, height, color, cfg, def_batch, desc = WORKLOADS[args.workload]
+    cfg = resolve_cfg(cfg)
+    batch = args.batch or def_batch
+    bpp = BPP[color]
+    img_bytes = width * height * bpp
+    mp_per_step = batch * width * height / 1e6
+
+    n_distinct = min(DISTINCT, batch)
+    frames = frames_for(width, height, color, n_distinct)
+    # rank r starts its repeat cycle at a different frame so ranks do not encode identical batches
+    order = [(i + rank) % n_distinct for i in range(batch)]
+
+    stream = torch.cuda.current_stream()
+    device = je.Device(local, cuda_stream=stream.cuda_stream)
+    enc = make_encoder(cfg, device)
+    ct = CT[color][1]
+
+    # inputs resident in HBM (image stride padded to 256 B)
+    stride = (img_bytes + 255) & ~255
+    d_in = torch.empty(batch * stride, dtype=torch.uint8, device=dev_t)
+    d_distinct = [torch.from_numpy(f.reshape(-1)).to(dev_t) for f in frames]
+    for i, k in enumerate(order):
+        d_in[i * stride:i * stride + img_bytes].copy_(d_distinct[k])
+    torch.cuda.synchronize()
+
+    # parity gate: the bytes this run produces must equal the oracle's (un-timed)
+    d_files, offs = enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
+    total = offs[-1]
+    from cases import oracle_encode
+    check = sorted(set([0, batch // 2, batch - 1]))[:3]
+    outs = enc.encode_batch([frames[order[i]] for i in check], width, height, ct)
+    for i, o in zip(check, outs):
+        want = oracle_encode(frames[order[i]], width, height, color, cfg)
+        if o != want:
+            raise SystemExit("bench.py: GPU bytes differ from the oracle for frame %d -- number would be invalid" % i)
+        if len(o) != offs[i + 1] - offs[i]:
+            raise SystemExit("bench.py: device-batch file size differs from the host-batch one for frame %d" % i)
+    out_bytes_per_step = int(total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    device.set_timing(True)
+    for _ in range(args.warmup):
+        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
+        launches += device.last_launch_count()
+        for k, v in (device.last_timing() or {}).items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = mp_per_step * world / (ms_per_step / 1e3)
+
+    # ---- end to end through the host-buffer C ABI (pinned pixels in, host bytes out) ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    pinned = [torch.from_numpy(f.reshape(-1)).pin_memory() for f in frames]
+    ptrs = (C.c_void_p * batch)(*[pinned[k].data_ptr() for k in order])
+    outs_c = (C.POINTER(C.c_uint8) * batch)()
+    lens_c = (C.c_size_t * batch)()
+    p = enc._params(width, height, ct)
+    lib = device.lib
+
+    def e2e_step():
+        rc = lib.jpgb_encode_batch(device.handle, C.byref(p), ptrs, img_bytes, batch, outs_c, lens_c)
+        if rc != 0:
+            raise SystemExit("bench.py: jpgb_encode_batch failed: %s" % device.last_error())
+        n = sum(lens_c[i] for i in range(batch))
+        for i in range(batch):
+            lib.jpgb_free(outs_c[i])
+        return n
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        d2h = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = mp_per_step * world * e2e_steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (colour + DCT + quant) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    a_bytes = stage_a_bytes(width, height, color, cfg) * batch
+    a_ms = stage_ms.get("colour_dct_quant", 0.0) / args.steps
+    achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "stage_a_kernel (colour+decimate+fDCT+quant)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": a_bytes, "ms_per_launch": a_ms,
+                "share_of_step": a_ms / ms_per_step if ms_per_step else None}
+    traffic_path = os.path.join(ROOT, "profiles", "stage_a_traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            tr = json.load(open(traffic_path))
+            if tr.get("workload") == args.workload:
+                roofline["traffic"] = tr.get("dram_bytes_per_launch_scaled_to_batch", {}).get(str(batch))
+        except (ValueError, OSError):
+            pass
+
+    # ---- CPU baseline on a bounded sample of the same workload ----
+    cpu = None
+    if not args.no_cpu:
+        cores = usable_cores()
+        v1, n1 = cpu_encode_rate(frames, width, height, color, cfg, args.cpu_seconds / 3.0, 1)
+        vN, nN = cpu_encode_rate(frames, width, height, color, cfg, args.cpu_seconds, cores)
+        cpu = {"value": vN, "unit": "megapixels/s", "cores": cores, "kind": "port",
+               "sample": "%d encodes of the workload's frames, one encode per thread on %d threads (%.0f s); single thread: %d encodes"
+                         % (nN, cores, args.cpu_seconds, n1),
+               "single_thread_value": v1,
+               "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native; the Rust crate cannot be built in this image"}
+
+    line = {
+        "metric": "megapixels/sec encoded, byte-identical to the reference restatement",
+        "value": value, "unit": "megapixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 in / i32 arithmetic / i16 coefficients", "data": "synthetic",
+        "config": {"workload": desc, "workload_id": args.workload, "frames_per_gpu": batch, "width": width, "height": height,
+                   "settings": {k: (v if k != "qtables" else "custom u16[64] x2") for k, v in cfg.items()},
+                   "distinct_frames": n_distinct, "bytes_out_per_step_per_gpu": out_bytes_per_step,
+                   "l2": "inputs (%.1f MB per step per GPU) larger than L2, no flush" % (batch * img_bytes / 1e6)
+                   if batch * img_bytes > 200e6 else "inputs smaller than L2 (%.1f MB): single-image latency case" % (batch * img_bytes / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": batch * img_bytes * world,
+                "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "api": "jpgb_encode_batch (pinned host pixels -> host JPEG bytes)"},
+        "gpu_launches": launches,
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---- the reference arm: the CPU restatement on the host cores -------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    width, height, color, cfg, def_batch, desc = WORKLOADS[args.workload]
+    cfg = resolve_cfg(cfg)
+    n_distinct = min(DISTINCT, args.batch or def_batch)
+    frames = frames_for(width, height, color, n_distinct)
+    cores = usable_cores()
+    per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_encode_rate(frames, width, height, color, cfg, min(per_step, 2.0), cores)
+    t0 = time.perf_counter()
+    mp = 0.0
+    n_enc = 0
+    for _ in range(args.steps):
+        v, n = cpu_encode_rate(frames, width, height, color, cfg, per_step, cores)
+        n_enc += n
+        mp += n * width * height / 1e6
+    dt = time.perf_counter() - t0
+    value = mp / dt
+    sample = "%d encodes of the workload's frames per run, one encode per thread on %d threads, %.1f s per step" % (n_enc, cores, per_step)
+    line = {
+        "impl": "reference", "metric": "megapixels/sec encoded, byte-identical to the reference restatement",
+        "value": value, "unit": "megapixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 in / i32 arithmetic / i16 coefficients", "data": "synthetic",
+        "config": {"workload": desc, "workload_id": args.workload, "width": width, "height": height,
+                   "settings": {k: (v if k != "qtables" else "custom u16[64] x2") for k, v in cfg.items()}},
+        "cpu_baseline": {"value": value, "unit": "megapixels/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native; no Rust toolchain in the image"},
+        "e2e": {"value": value, "unit": "megapixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,7 @@
 namespace jpgb {
 
 constexpr int kMaxScans = 256;  // 4 components x 64 progressive scans
-constexpr int kMaxSlots = 12;   // blocks per interleaved MCU: 8 (luma 2x4) + 2, or 3 + 8 for CMYK
+constexpr int kMaxSlots = 20;   // blocks per MCU-sized unit: YCCK at F_4_2 / F_2_4 has 8 + 1 + 1 + 8 = 18
 
 // Quantizer constants per table, natural order. q = (v*mul + (v < 0 ? add_neg : add_pos)) >> 16
 // reproduces `((abs(v) + corr) * recip) >> 15` with the sign re-applied (src/quantization.rs:291-307):

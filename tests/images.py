@@ -70,3 +70,26 @@ def photo_like(width, height, channels=3, seed=42):
         planes.append(np.clip(base + tex + noise, 0, 255).astype(np.uint8))
     img = np.stack(planes, axis=-1)
     return img[..., 0] if channels == 1 else img
+
+
+def synth_frame(width, height, channels=3, seed=0):
+    """Integer-only photo-like frame (exactly reproducible everywhere): two triangular-wave gradients
+    per channel, a fine diagonal texture and +-4 of hashed noise. Compresses to ~0.2-0.3 B/px at q90 4:2:0."""
+    y = np.arange(height, dtype=np.int64)[:, None]
+    x = np.arange(width, dtype=np.int64)[None, :]
+
+    def tri(t, period):
+        t = t % period
+        return np.abs(t - period // 2) * 510 // period  # 0..255
+
+    planes = []
+    for c in range(channels):
+        a = tri(x * (3 + c) + y * (2 + seed % 5) + seed * 131 + c * 977, 2048 + 256 * c)
+        b = tri(x * (1 + (seed >> 2) % 3) - y * (4 + c) + seed * 29, 1536 + 128 * (seed % 7))
+        t = tri(x * 37 + y * 53 + c * 11, 64) >> 3
+        hsh = (x * 0x9E3779B1 + y * 0x85EBCA77 + (seed * 4 + c) * 0xC2B2AE3D) & 0xFFFFFFFF
+        hsh = (hsh ^ (hsh >> 15)) * 0x2C1B3C6D & 0xFFFFFFFF
+        n = ((hsh >> 13) & 7) - 4
+        planes.append(np.clip((a * 5 + b * 3) // 8 + t + n - 12, 0, 255).astype(np.uint8))
+    img = np.stack(planes, axis=-1)
+    return img[..., 0] if channels == 1 else img

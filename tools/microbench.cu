@@ -19,13 +19,19 @@ __global__ void k(unsigned *out, unsigned a0, unsigned b0) {
             if (OP == 1) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(b), "r"(0x01020304u));
             if (OP == 2) asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(b), "r"(0x01020304u));
             if (OP == 3) x[i] = __byte_perm(x[i], b, 0x7632);            // PRMT
-            if (OP == 4) x[i] = (x[i] >> 3) + 0;                          // SHF / shift
-            if (OP == 5) x[i] = (x[i] & b) ^ 0x55aa55aa;                  // LOP3
-            if (OP == 6) x[i] = x[i] + b + 0x33;                          // IADD3
+            if (OP == 4) asm volatile("shr.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b & 1));     // SHF
+            if (OP == 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(x[i]) : "r"(b), "r"(0x55aa55aau)); // LOP3
+            if (OP == 6) asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b));          // IADD
             if (OP == 7) x[i] = ((int)x[i] < 0) ? b : x[i] + 1;           // ISETP+SEL-ish
             if (OP == 8) asm volatile("dp2a.hi.s32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(b), "r"(0x01020304u));
             if (OP == 9) x[i] = __funnelshift_r(x[i], b, 15);             // SHF.R funnel
             if (OP == 10) x[i] = abs((int)x[i]) + 1;                      // IABS
+            if (OP == 12) { asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(b), "r"(0x01020304u)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(x[i]) : "r"(b), "r"(0x55aa55aau)); }
+            if (OP == 13) { asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(b), "r"(0x01020304u)); x[i] = x[i] * b + 0x1234; }
+            if (OP == 14) { asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b)); x[i] = x[i] * b + 0x1234; }
+            if (OP == 15) { asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(x[i]) : "r"(b)); x[i] = x[i] * b + 0x1234; }
+            if (OP == 16) { asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(x[i]) : "r"(b)); asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b)); }
+            if (OP == 17) { asm volatile("mad.lo.s32 %0, %0, 1, %1;" : "+r"(x[i]) : "r"(b)); asm volatile("add.s32 %0, %0, %1;" : "+r"(x[i]) : "r"(b)); }
             if (OP == 11) { x[i] = x[i] * b + 0x1234; x[i] = (x[i] >> 3) ^ b; } // IMAD + LOP/SHF pair (dual pipe)
         }
     }
@@ -73,6 +79,12 @@ int main() {
     run<9>("SHF funnel", d, sms);
     run<10>("IABS+IADD", d, sms, 2.0);
     run<11>("IMAD + SHF + LOP3 mix", d, sms, 3.0);
+    run<12>("IDP.2A + LOP3", d, sms, 2.0);
+    run<13>("IDP.2A + IMAD", d, sms, 2.0);
+    run<14>("IADD + IMAD", d, sms, 2.0);
+    run<15>("PRMT + IMAD", d, sms, 2.0);
+    run<16>("PRMT + IADD", d, sms, 2.0);
+    run<17>("mad(x,1,b) + IADD", d, sms, 2.0);
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
