@@ -396,16 +396,19 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
 
 // byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
 // bytes that precede it
-__global__ void file_offsets_kernel(const EntropyBuffers b, unsigned n_images, unsigned long long bytes) {
-    const unsigned img = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers b, unsigned n_images, unsigned long long bytes) {
+    // one warp per file boundary; lanes stride over the (< kStuffChunk) bytes between the chunk start and it
+    const unsigned img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (img > n_images) return;
     const DevPlan &P = *b.plan;
     const unsigned long long pos = img == n_images ? bytes : b.segpos[(unsigned long long)img * P.segs_per_image];
     const unsigned long long chunk = pos / kStuffChunk;
-    unsigned long long ff = pos == bytes && chunk * kStuffChunk == pos ? b.ffpos[chunk] : b.ffpos[chunk];
-    for (unsigned long long i = chunk * kStuffChunk; i < pos; ++i)
+    unsigned ff = 0;
+    for (unsigned long long i = chunk * kStuffChunk + lane; i < pos; i += 32)
         if (b.ustream[i] == 0xFF && !((b.raw_mask[i >> 5] >> (i & 31)) & 1u)) ++ff;
-    b.file_off[img] = pos + ff;
+    ff = __reduce_add_sync(0xffffffffu, ff);
+    if (lane == 0) b.file_off[img] = pos + b.ffpos[chunk] + ff;
 }
 
 // ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
@@ -530,7 +533,7 @@ cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t bytes, cudaSt
     return cudaGetLastError();
 }
 cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, uint64_t bytes, cudaStream_t s) {
-    file_offsets_kernel<<<grid_for(n + 1ull, 128), 128, 0, s>>>(b, n, bytes);
+    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, n, bytes);
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 #include "host.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace jpgb {
@@ -457,6 +458,8 @@ void Plan::fill_device_plan(DevPlan &d) const {
     }
 }
 
+bool force_generic_stage_a = false; // test hook: route every format through the generic kernel
+
 void Plan::fill_stage_a(StageAParams &a) const {
     std::memset(&a, 0, sizeof(a));
     a.blocks_per_image = blocks_per_image;
@@ -485,6 +488,12 @@ void Plan::fill_stage_a(StageAParams &a) const {
             }
     }
     a.tasks_per_group = n;
+    // Fast kernel: Luma, the RGB family and CmykAsYcck with luma factors in {1,2}. Same number of warp
+    // tasks per 32-MCU group; a task is then (component, v, run of 32 consecutive blocks).
+    const bool fast_ct = p.color_type == JPGB_LUMA || (p.color_type >= JPGB_RGB && p.color_type <= JPGB_BGRA) ||
+                         p.color_type == JPGB_CMYK_AS_YCCK;
+    const char *fg = std::getenv("JPGB_FORCE_GENERIC_STAGE_A"); // test hook
+    a.use_fast = fast_ct && hmax <= 2 && vmax <= 2 && !force_generic_stage_a && !(fg && fg[0] == '1');
     // CTA tile: `groups` x 32 MCUs wide, one MCU row high; aim for ~24 KB of pixels in shared memory
     const int group_bytes = 32 * 8 * hmax * 8 * vmax * bpp;
     int g = std::max(1, 24576 / group_bytes);

@@ -15,6 +15,8 @@
 // shuffles, no shared-memory round trip, no divergence. Each lane then writes its 128-byte block.
 //
 // All arithmetic is 32-bit integer; tensor cores are not used (the DCT must be bit-exact).
+#include <utility>
+
 #include "kernels.h"
 
 namespace jpgb {
@@ -189,6 +191,288 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
     }
 }
 
+
+// =================================================================================================
+// Fast path (the BASELINE configurations): Luma, the RGB family and CmykAsYcck at luma sampling
+// 1x1 / 2x1 / 1x2 / 2x2. Same tile, same one-block-per-lane decomposition, but
+//   * a warp task is 32 *consecutive blocks of one component block row*, so the 32 lanes read
+//     adjacent 8-pixel spans (bank-conflict-free 64/128-bit shared loads) and write one contiguous
+//     4 KB run of coefficients with 256-bit stores;
+//   * colour conversion runs on packed pixel words with IDP.2A (dp2a: two 16-bit coefficients x
+//     two pixel bytes + accumulator per instruction), measured on B200 at the same 64 lanes/clk/SM
+//     as IMAD (profiles/r1_int_pipe_microbench.txt): 2 IDP + 1 shift per Y sample, no byte
+//     extraction. The arithmetic is the reference's: the same integer sum, + 0x7FFF, >> 16.
+// =================================================================================================
+
+// acc + CA * byte(2*HI) + CB * byte(2*HI+1) of w, exactly, for compile-time coefficients.
+template <int CA, int CB, bool HI>
+__device__ __forceinline__ int idp2(int acc, uint32_t w) {
+    constexpr bool fits_u = CA >= 0 && CB >= 0 && CA <= 65535 && CB <= 65535;
+    constexpr bool fits_s = CA >= -32768 && CA <= 32767 && CB >= -32768 && CB <= 32767;
+    if constexpr (CA == 0 && CB == 0) {
+        return acc;
+    } else if constexpr (fits_u) {
+        constexpr uint32_t c = (uint32_t)CA | ((uint32_t)CB << 16);
+        int r;
+        if constexpr (HI) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(w), "r"(acc));
+        else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(w), "r"(acc));
+        return r;
+    } else if constexpr (fits_s) {
+        constexpr uint32_t c = ((uint32_t)CA & 0xFFFFu) | (((uint32_t)CB & 0xFFFFu) << 16);
+        int r;
+        if constexpr (HI) asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(w), "r"(acc));
+        else asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(w), "r"(acc));
+        return r;
+    } else { // one coefficient needs the signed, the other the unsigned 16-bit range: two instructions
+        return idp2<CA, 0, HI>(idp2<0, CB, HI>(acc, w), w);
+    }
+}
+
+// K + M0*b[O] + M1*b[O+1] + M2*b[O+2] where b[] are the bytes of the word array w (register
+// resident, compile-time indices). Three consecutive bytes always straddle exactly two byte pairs.
+template <int O, int M0, int M1, int M2, int K, int NW>
+__device__ __forceinline__ int dot3(const uint32_t (&w)[NW]) {
+    constexpr int P0 = O >> 1, P1 = (O + 2) >> 1; // byte-pair indices
+    constexpr int A0 = (2 * P0 == O) ? M0 : 0;    // coefficient of pair P0 slot 0
+    constexpr int B0 = (2 * P0 + 1 == O) ? M0 : ((2 * P0 + 1 == O + 1) ? M1 : 0);
+    constexpr int A1 = (2 * P1 == O + 1) ? M1 : ((2 * P1 == O + 2) ? M2 : 0);
+    constexpr int B1 = (2 * P1 + 1 == O + 2) ? M2 : 0;
+    int acc = K;
+    acc = idp2<A0, B0, (P0 & 1) != 0>(acc, w[P0 >> 1]);
+    acc = idp2<A1, B1, (P1 & 1) != 0>(acc, w[P1 >> 1]);
+    return acc;
+}
+
+enum Role { ROLE_Y = 0, ROLE_CB = 1, ROLE_CR = 2, ROLE_K = 3, ROLE_RAW = 4 };
+
+template <int CT>
+struct Fmt {
+    static constexpr int BPP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR) ? 3 : 4);
+    static constexpr bool BGR = CT == JPGB_BGR || CT == JPGB_BGRA;
+};
+
+// sample I of a block row from the row's pixel words (compile-time I: every byte offset is static)
+template <int CT, int ROLE, int SX, int I, int NW>
+__device__ __forceinline__ int sample_at(const uint32_t (&w)[NW]) {
+    constexpr int BPP = Fmt<CT>::BPP;
+    constexpr int RND = 0x7FFF, MID = (128 << 16) + 0x7FFF;
+    constexpr int O = I * SX * BPP; // byte offset of the pixel inside w
+    if constexpr (ROLE == ROLE_RAW) {
+        return (int)__byte_perm(w[O >> 2], 0, 0x4440 + (O & 3));
+    } else if constexpr (ROLE == ROLE_K) { // 255 - k, image_buffer.rs:35-38
+        return (int)__byte_perm(~w[(O + 3) >> 2], 0, 0x4440 + ((O + 3) & 3));
+    } else if constexpr (ROLE == ROLE_Y) {
+        // Y = (19595 R + 38470 G + 7471 B + 0x7FFF) >> 16            image_buffer.rs:22,26
+        if constexpr (Fmt<CT>::BGR) return dot3<O, 7471, 38470, 19595, RND>(w) >> 16;
+        else return dot3<O, 19595, 38470, 7471, RND>(w) >> 16;
+    } else if constexpr (ROLE == ROLE_CB) {
+        // Cb = (-11059 R - 21709 G + 32768 B + (128 << 16) + 0x7FFF) >> 16   :23,27
+        if constexpr (Fmt<CT>::BGR) return dot3<O, 32768, -21709, -11059, MID>(w) >> 16;
+        else return dot3<O, -11059, -21709, 32768, MID>(w) >> 16;
+    } else {
+        // Cr = (32768 R - 27439 G - 5329 B + (128 << 16) + 0x7FFF) >> 16     :24,28
+        if constexpr (Fmt<CT>::BGR) return dot3<O, -5329, -27439, 32768, MID>(w) >> 16;
+        else return dot3<O, 32768, -27439, -5329, MID>(w) >> 16;
+    }
+}
+template <int CT, int ROLE, int SX, int NW, int... Is>
+__device__ __forceinline__ void sample_row(const uint32_t (&w)[NW], int *s, std::integer_sequence<int, Is...>) {
+    ((s[Is] = sample_at<CT, ROLE, SX, Is, NW>(w)), ...);
+}
+
+// 8 samples (unshifted, 0..255) of one block row. `row` points at the first pixel of the row in the
+// shared tile; the pixels used are 0, SX, 2*SX, ... (point decimation, encoder.rs:1222-1242).
+template <int CT, int ROLE, int SX>
+__device__ __forceinline__ void load_row(const uint8_t *row, int *s) {
+    constexpr int BPP = Fmt<CT>::BPP;
+    constexpr int NW = (((7 * SX + 1) * BPP) + 3) / 4; // words spanned
+    uint32_t w[NW];
+    if constexpr (BPP == 1) {
+        const uint2 a = *reinterpret_cast<const uint2 *>(row);
+        w[0] = a.x;
+        w[1] = a.y;
+    } else if constexpr (BPP == 3 && SX == 1) {
+        const uint2 *r = reinterpret_cast<const uint2 *>(row);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint2 a = r[i];
+            w[2 * i] = a.x;
+            w[2 * i + 1] = a.y;
+        }
+    } else if constexpr (BPP == 3 && SX == 2) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint4 a = r[i];
+            w[4 * i] = a.x;
+            w[4 * i + 1] = a.y;
+            w[4 * i + 2] = a.z;
+            if (4 * i + 3 < NW) w[4 * i + 3] = a.w;
+        }
+    } else if constexpr (BPP == 4 && SX == 1) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 a = r[i];
+            w[4 * i] = a.x;
+            w[4 * i + 1] = a.y;
+            w[4 * i + 2] = a.z;
+            w[4 * i + 3] = a.w;
+        }
+    } else { // BPP == 4, SX == 2: every other pixel word
+        const uint32_t *r = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[2 * i] = r[2 * i];
+    }
+    sample_row<CT, ROLE, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
+}
+
+template <int CT, int ROLE, int SX, int SY>
+__device__ __forceinline__ void load_block(const uint8_t *base, int pitch, int (&v)[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) load_row<CT, ROLE, SX>(base + y * SY * pitch, &v[y * 8]);
+}
+
+__device__ __forceinline__ void store256(void *dst, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                         uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+                 "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
+
+template <int T>
+__device__ __forceinline__ void quantize_store256(const StageAParams &p, const int (&v)[64], int16_t *dst) {
+    constexpr ZZ zz = make_zz();
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i0 = w * 16 + k * 2, i1 = i0 + 1;
+            const int a = quant32<T>(p, v[zz.v[i0]], zz.v[i0]);
+            const int b = quant32<T>(p, v[zz.v[i1]], zz.v[i1]);
+            r[k] = __byte_perm((uint32_t)a, (uint32_t)b, 0x7632);
+        }
+        store256(dst + w * 16, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+    }
+}
+
+// HS x VS = sampling factor of the full-resolution components (luma, K); the others are 1x1.
+template <int CT, int HS, int VS>
+__global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    constexpr int BPP = Fmt<CT>::BPP;
+    const int tile_x = blockIdx.x, mcu_y = blockIdx.y, img = blockIdx.z;
+    const int mcu_x0 = tile_x * 32 * p.groups;
+    const int px0 = mcu_x0 * 8 * HS, py0 = mcu_y * 8 * VS;
+    const uint8_t *src = p.pixels + (size_t)img * p.image_stride;
+    const size_t row_bytes = (size_t)p.width * BPP;
+    const int pitch = p.tile_pitch;
+
+    // ---- stage the tile with 128-bit coalesced loads; edges replicated while staging (Q4) ----
+    {
+        const int chunks_per_row = pitch / 16;
+        const int n_chunks = chunks_per_row * (8 * VS);
+        const int valid_px = min(p.tile_w_px, p.width - px0);
+        const int valid_bytes = valid_px * BPP;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(src) + (size_t)px0 * BPP) & 15) == 0 && (row_bytes & 15) == 0;
+        for (int c0 = threadIdx.x; c0 < n_chunks; c0 += blockDim.x * 4) {
+            uint4 q[4];
+            bool fast[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { // issue up to four independent 16-byte loads before the first store
+                const int c = c0 + u * blockDim.x;
+                fast[u] = false;
+                if (c < n_chunks) {
+                    const int ry = c / chunks_per_row, cb = (c - ry * chunks_per_row) * 16;
+                    const int sy = min(py0 + ry, p.height - 1);
+                    const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+                    if (aligned && cb + 16 <= valid_bytes) {
+                        q[u] = __ldg(reinterpret_cast<const uint4 *>(row + cb));
+                        fast[u] = true;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * blockDim.x;
+                if (c >= n_chunks) continue;
+                const int ry = c / chunks_per_row, cb = (c - ry * chunks_per_row) * 16;
+                uint8_t *dst = tile + ry * pitch + cb;
+                if (fast[u]) {
+                    *reinterpret_cast<uint4 *>(dst) = q[u];
+                } else {
+                    const int sy = min(py0 + ry, p.height - 1);
+                    const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+                    for (int b = 0; b < 16; ++b) {
+                        const int byte = cb + b;
+                        const int px = byte / BPP, ch = byte - px * BPP;
+                        dst[b] = row[min(px, valid_px - 1) * BPP + ch];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int n_tasks = p.groups * p.tasks_per_group;
+    for (int task = warp; task < n_tasks; task += n_warps) {
+        const int group = task / p.tasks_per_group, slot = task - group * p.tasks_per_group;
+        const int comp = p.task_comp[slot], bv = p.task_v[slot], sub = p.task_h[slot];
+        const int H = p.comp_h[comp], V = p.comp_v[comp];
+        const bool full = H == HS && V == VS;
+        // block column inside the tile's block row of this component, then in the image
+        const int bx_local = (group * H + sub) * 32 + lane;
+        const int bx = mcu_x0 * H + bx_local;
+        if (bx >= p.comp_pw[comp]) continue;
+        const uint8_t *base = full ? tile + (bv * 8) * pitch + bx_local * 8 * BPP : tile + bx_local * 8 * HS * BPP;
+
+        int v[64];
+        if (CT == JPGB_LUMA) {
+            load_block<CT, ROLE_RAW, 1, 1>(base, pitch, v);
+        } else if (full) {
+            if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
+            else if (comp == 3) load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
+            else if (comp == 1) load_block<CT, ROLE_CB, 1, 1>(base, pitch, v); // only when HS == VS == 1
+            else load_block<CT, ROLE_CR, 1, 1>(base, pitch, v);
+        } else {
+            if (comp == 1) load_block<CT, ROLE_CB, HS, VS>(base, pitch, v);
+            else load_block<CT, ROLE_CR, HS, VS>(base, pitch, v);
+        }
+
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+            dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+            dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
+
+        const size_t blk = (size_t)img * p.blocks_per_image + p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_pw[comp] + bx;
+        int16_t *dst = p.coef + blk * 64;
+        if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
+        else quantize_store256<1>(p, v, dst);
+    }
+}
+
+template <int CT, int HS, int VS>
+cudaError_t launch_fast(const StageAParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(stage_a_fast_kernel<CT, HS, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    stage_a_fast_kernel<CT, HS, VS><<<grid, block, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int CT>
+cudaError_t launch_fast_ct(const StageAParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    if (p.hmax == 1 && p.vmax == 1) return launch_fast<CT, 1, 1>(p, grid, block, smem, stream);
+    if (p.hmax == 2 && p.vmax == 1) return launch_fast<CT, 2, 1>(p, grid, block, smem, stream);
+    if (p.hmax == 1 && p.vmax == 2) return launch_fast<CT, 1, 2>(p, grid, block, smem, stream);
+    return launch_fast<CT, 2, 2>(p, grid, block, smem, stream);
+}
+
 } // namespace
 
 cudaError_t launch_stage_a(const StageAParams &p, uint32_t n_images, cudaStream_t stream) {
@@ -196,6 +480,17 @@ cudaError_t launch_stage_a(const StageAParams &p, uint32_t n_images, cudaStream_
     const int n_tasks = p.groups * p.tasks_per_group;
     const int warps = n_tasks < 8 ? n_tasks : 8;
     dim3 grid(p.tiles_per_row, p.mcu_rows, n_images), block(warps * 32);
+    if (p.use_fast) {
+        switch (p.color_type) {
+        case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, grid, block, smem, stream);
+        case JPGB_RGB: return launch_fast_ct<JPGB_RGB>(p, grid, block, smem, stream);
+        case JPGB_RGBA: return launch_fast_ct<JPGB_RGBA>(p, grid, block, smem, stream);
+        case JPGB_BGR: return launch_fast_ct<JPGB_BGR>(p, grid, block, smem, stream);
+        case JPGB_BGRA: return launch_fast_ct<JPGB_BGRA>(p, grid, block, smem, stream);
+        case JPGB_CMYK_AS_YCCK: return launch_fast_ct<JPGB_CMYK_AS_YCCK>(p, grid, block, smem, stream);
+        default: break;
+        }
+    }
 #define JPGB_LAUNCH_A(CT)                                                                                        \
     case CT: {                                                                                                   \
         if (smem > 48 * 1024) {                                                                                  \

@@ -55,6 +55,19 @@ def test_stage_a_coefficients(color, sampling):
         np.testing.assert_array_equal(got[o:o + n], want[c], err_msg="component %d" % c)
 
 
+def test_generic_and_fast_stage_a_kernels_agree(monkeypatch):
+    """Formats served by the fast kernel must also be exact through the generic one (and vice versa)."""
+    for color, sampling in (("rgb", (2, 2)), ("bgr", (2, 1)), ("rgba", (1, 2)), ("bgra", (1, 1)), ("luma", (1, 1)),
+                            ("cmyk_as_ycck", (2, 2)), ("cmyk_as_ycck", (1, 1))):
+        cfg = dict(quality=83, sampling=sampling)
+        img = _img(color, 333, 77, seed=11)
+        want = oracle_encode(img, 333, 77, color, cfg)
+        assert gpu_encode(img, 333, 77, color, cfg) == want
+        monkeypatch.setenv("JPGB_FORCE_GENERIC_STAGE_A", "1")
+        assert gpu_encode(img, 333, 77, color, cfg) == want
+        monkeypatch.delenv("JPGB_FORCE_GENERIC_STAGE_A")
+
+
 # ---- the reference's own end-to-end cases (src/lib.rs:188-553), now compared on bytes -----------
 REF_RGB_CASES = {
     "rgb_100": dict(quality=100),
