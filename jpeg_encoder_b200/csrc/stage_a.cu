@@ -357,137 +357,175 @@ __device__ __forceinline__ void quantize_store256(const StageAParams &p, const i
     }
 }
 
-// HS x VS = sampling factor of the full-resolution components (luma, K); the others are 1x1.
-template <int CT, int HS, int VS>
-__global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
-    extern __shared__ __align__(16) uint8_t tile[];
-    constexpr int BPP = Fmt<CT>::BPP;
-    const int tile_x = blockIdx.x, mcu_y = blockIdx.y, img = blockIdx.z;
-    const int mcu_x0 = tile_x * 32 * p.groups;
-    const int px0 = mcu_x0 * 8 * HS, py0 = mcu_y * 8 * VS;
-    const uint8_t *src = p.pixels + (size_t)img * p.image_stride;
-    const size_t row_bytes = (size_t)p.width * BPP;
-    const int pitch = p.tile_pitch;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-    // ---- stage the tile with 128-bit coalesced loads; edges replicated while staging (Q4) ----
-    {
-        const int chunks_per_row = pitch / 16;
-        const int n_chunks = chunks_per_row * (8 * VS);
-        const int valid_px = min(p.tile_w_px, p.width - px0);
-        const int valid_bytes = valid_px * BPP;
-        const bool aligned = ((reinterpret_cast<uintptr_t>(src) + (size_t)px0 * BPP) & 15) == 0 && (row_bytes & 15) == 0;
-        for (int c0 = threadIdx.x; c0 < n_chunks; c0 += blockDim.x * 4) {
-            uint4 q[4];
-            bool fast[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { // issue up to four independent 16-byte loads before the first store
-                const int c = c0 + u * blockDim.x;
-                fast[u] = false;
-                if (c < n_chunks) {
-                    const int ry = c / chunks_per_row, cb = (c - ry * chunks_per_row) * 16;
-                    const int sy = min(py0 + ry, p.height - 1);
-                    const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
-                    if (aligned && cb + 16 <= valid_bytes) {
-                        q[u] = __ldg(reinterpret_cast<const uint4 *>(row + cb));
-                        fast[u] = true;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + u * blockDim.x;
-                if (c >= n_chunks) continue;
-                const int ry = c / chunks_per_row, cb = (c - ry * chunks_per_row) * 16;
-                uint8_t *dst = tile + ry * pitch + cb;
-                if (fast[u]) {
-                    *reinterpret_cast<uint4 *>(dst) = q[u];
-                } else {
-                    const int sy = min(py0 + ry, p.height - 1);
-                    const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
-                    for (int b = 0; b < 16; ++b) {
-                        const int byte = cb + b;
-                        const int px = byte / BPP, ch = byte - px * BPP;
-                        dst[b] = row[min(px, valid_px - 1) * BPP + ch];
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
+struct TileCoord {
+    int img, mcu_y, mcu_x0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const StageAParams &p, unsigned t) {
+    TileCoord c;
+    const unsigned tx = t % (unsigned)p.tiles_per_row, r = t / (unsigned)p.tiles_per_row;
+    c.mcu_y = (int)(r % (unsigned)p.mcu_rows);
+    c.img = (int)(r / (unsigned)p.mcu_rows);
+    c.mcu_x0 = (int)tx * 32 * p.groups;
+    return c;
+}
 
+// Stage one tile (8*VS pixel rows x tile_pitch bytes) into shared memory. Whole 16-byte chunks inside
+// the image go through cp.async (LDGSTS, L2 only: the pixels are read exactly once); chunks that hold
+// the right edge are filled byte-wise with the row's last pixel replicated (Q4: encoder.rs:738-744);
+// chunks past the last MCU of the row are never read and are skipped. Rows past the bottom re-read
+// the last image row (:734). Warps take rows, lanes take chunks: no divisions.
+template <int BPP, int VS>
+__device__ __forceinline__ void stage_tile(const StageAParams &p, const TileCoord tc, uint8_t *tile) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int n_tasks = p.groups * p.tasks_per_group;
-    for (int task = warp; task < n_tasks; task += n_warps) {
-        const int group = task / p.tasks_per_group, slot = task - group * p.tasks_per_group;
-        const int comp = p.task_comp[slot], bv = p.task_v[slot], sub = p.task_h[slot];
-        const int H = p.comp_h[comp], V = p.comp_v[comp];
-        const bool full = H == HS && V == VS;
-        // block column inside the tile's block row of this component, then in the image
-        const int bx_local = (group * H + sub) * 32 + lane;
-        const int bx = mcu_x0 * H + bx_local;
-        if (bx >= p.comp_pw[comp]) continue;
-        const uint8_t *base = full ? tile + (bv * 8) * pitch + bx_local * 8 * BPP : tile + bx_local * 8 * HS * BPP;
-
-        int v[64];
-        if (CT == JPGB_LUMA) {
-            load_block<CT, ROLE_RAW, 1, 1>(base, pitch, v);
-        } else if (full) {
-            if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
-            else if (comp == 3) load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
-            else if (comp == 1) load_block<CT, ROLE_CB, 1, 1>(base, pitch, v); // only when HS == VS == 1
-            else load_block<CT, ROLE_CR, 1, 1>(base, pitch, v);
-        } else {
-            if (comp == 1) load_block<CT, ROLE_CB, HS, VS>(base, pitch, v);
-            else load_block<CT, ROLE_CR, HS, VS>(base, pitch, v);
+    const int px0 = tc.mcu_x0 * 8 * p.hmax, py0 = tc.mcu_y * 8 * VS;
+    const uint8_t *src = p.pixels + (size_t)tc.img * p.image_stride;
+    const size_t row_bytes = (size_t)p.width * BPP;
+    const int valid_px = min(p.tile_w_px, p.width - px0);
+    const int valid_bytes = valid_px * BPP;
+    const int needed_bytes = min(p.tile_w_px, p.mcu_cols * 8 * p.hmax - px0) * BPP; // through the last MCU of the row
+    for (int ry = warp; ry < 8 * VS; ry += n_warps) {
+        const int sy = min(py0 + ry, p.height - 1);
+        const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+        uint8_t *dst = tile + ry * p.tile_pitch;
+        const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+        for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
+            if (aligned && cb + 16 <= valid_bytes) {
+                cp_async16(dst + cb, row + cb);
+            } else {
+                for (int b = 0; b < 16; ++b) {
+                    const int byte = cb + b;
+                    const int px = byte / BPP, ch = byte - px * BPP;
+                    dst[cb + b] = row[min(px, valid_px - 1) * BPP + ch];
+                }
+            }
         }
-
-#pragma unroll
-        for (int y = 0; y < 8; ++y)
-            dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
-#pragma unroll
-        for (int x = 0; x < 8; ++x)
-            dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
-
-        const size_t blk = (size_t)img * p.blocks_per_image + p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_pw[comp] + bx;
-        int16_t *dst = p.coef + blk * 64;
-        if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
-        else quantize_store256<1>(p, v, dst);
     }
 }
 
+// HS x VS = sampling factor of the full-resolution components (luma, K); the others are 1x1.
+// Persistent: each CTA walks tiles t = blockIdx.x, + gridDim.x, ... with two shared-memory buffers,
+// so the cp.async traffic of tile i+1 is in flight while the warps transform tile i.
 template <int CT, int HS, int VS>
-cudaError_t launch_fast(const StageAParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(stage_a_fast_kernel<CT, HS, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+__global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int BPP = Fmt<CT>::BPP;
+    constexpr bool SUB = HS * VS > 1;                         // are there subsampled (1x1) components?
+    constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
+    const int pitch = p.tile_pitch;
+    const unsigned tile_bytes = (unsigned)pitch * 8 * VS;
+    const unsigned n_tiles = (unsigned)p.tiles_per_row * p.mcu_rows * p.n_images;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int n_tasks = p.groups * p.tasks_per_group;
+
+    unsigned t = blockIdx.x;
+    if (t < n_tiles) stage_tile<BPP, VS>(p, tile_coord(p, t), smem);
+    cp_async_commit();
+    for (unsigned it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        uint8_t *tile = smem + (it & 1) * tile_bytes;
+        const unsigned nt = t + gridDim.x;
+        if (nt < n_tiles) stage_tile<BPP, VS>(p, tile_coord(p, nt), smem + ((it + 1) & 1) * tile_bytes);
+        cp_async_commit();
+        cp_async_wait<1>(); // everything but the group just committed has landed: tile `t` is complete
+        __syncthreads();
+
+        const TileCoord tc = tile_coord(p, t);
+        for (int task = warp; task < n_tasks; task += n_warps) {
+            const int group = task / p.tasks_per_group, slot = task - group * p.tasks_per_group;
+            const int comp = p.task_comp[slot], bv = p.task_v[slot], sub = p.task_h[slot];
+            const bool full = !SUB || comp == 0 || comp == 3;
+            const int H = full ? HS : 1, V = full ? VS : 1;
+            // block column inside the tile's block row of this component, then in the image
+            const int bx_local = (group * H + sub) * 32 + lane;
+            const int bx = tc.mcu_x0 * H + bx_local;
+            if (bx >= p.comp_pw[comp]) continue;
+            const uint8_t *base = full ? tile + (bv * 8) * pitch + bx_local * 8 * BPP : tile + bx_local * 8 * HS * BPP;
+
+            int v[64];
+            if constexpr (CT == JPGB_LUMA) {
+                load_block<CT, ROLE_RAW, 1, 1>(base, pitch, v);
+            } else if constexpr (SUB) {
+                if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
+                else if (comp == 1) load_block<CT, ROLE_CB, HS, VS>(base, pitch, v);
+                else if (NCOMP == 3 || comp == 2) load_block<CT, ROLE_CR, HS, VS>(base, pitch, v);
+                else load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
+            } else {
+                if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
+                else if (comp == 1) load_block<CT, ROLE_CB, 1, 1>(base, pitch, v);
+                else if (NCOMP == 3 || comp == 2) load_block<CT, ROLE_CR, 1, 1>(base, pitch, v);
+                else load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
+            }
+
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+                dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+                dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
+
+            const size_t blk = (size_t)tc.img * p.blocks_per_image + p.comp_off[comp] +
+                               (size_t)(tc.mcu_y * V + bv) * p.comp_pw[comp] + bx;
+            int16_t *dst = p.coef + blk * 64;
+            if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
+            else quantize_store256<1>(p, v, dst);
+        }
+        __syncthreads(); // every warp is done with this buffer before the next iteration refills it
     }
-    stage_a_fast_kernel<CT, HS, VS><<<grid, block, smem, stream>>>(p);
+    cp_async_wait<0>();
+}
+
+template <int CT, int HS, int VS>
+cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
+    static int ctas_per_sm = 0, n_sms = 0;
+    const size_t smem = 2 * tile_bytes;
+    auto kernel = stage_a_fast_kernel<CT, HS, VS>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, (int)block.x, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const unsigned long long n_tiles = (unsigned long long)p.tiles_per_row * p.mcu_rows * p.n_images;
+    unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm; // persistent: one resident wave
+    if (grid > n_tiles) grid = n_tiles;
+    kernel<<<(unsigned)grid, block, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int CT>
-cudaError_t launch_fast_ct(const StageAParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
-    if (p.hmax == 1 && p.vmax == 1) return launch_fast<CT, 1, 1>(p, grid, block, smem, stream);
-    if (p.hmax == 2 && p.vmax == 1) return launch_fast<CT, 2, 1>(p, grid, block, smem, stream);
-    if (p.hmax == 1 && p.vmax == 2) return launch_fast<CT, 1, 2>(p, grid, block, smem, stream);
-    return launch_fast<CT, 2, 2>(p, grid, block, smem, stream);
+cudaError_t launch_fast_ct(const StageAParams &p, dim3 block, size_t smem, cudaStream_t stream) {
+    if (p.hmax == 1 && p.vmax == 1) return launch_fast<CT, 1, 1>(p, block, smem, stream);
+    if (p.hmax == 2 && p.vmax == 1) return launch_fast<CT, 2, 1>(p, block, smem, stream);
+    if (p.hmax == 1 && p.vmax == 2) return launch_fast<CT, 1, 2>(p, block, smem, stream);
+    return launch_fast<CT, 2, 2>(p, block, smem, stream);
 }
 
 } // namespace
 
-cudaError_t launch_stage_a(const StageAParams &p, uint32_t n_images, cudaStream_t stream) {
+cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStream_t stream) {
+    StageAParams p = p_in;
+    p.n_images = (int)n_images;
     const size_t smem = (size_t)p.tile_pitch * p.tile_h_px;
     const int n_tasks = p.groups * p.tasks_per_group;
     const int warps = n_tasks < 8 ? n_tasks : 8;
     dim3 grid(p.tiles_per_row, p.mcu_rows, n_images), block(warps * 32);
     if (p.use_fast) {
         switch (p.color_type) {
-        case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, grid, block, smem, stream);
-        case JPGB_RGB: return launch_fast_ct<JPGB_RGB>(p, grid, block, smem, stream);
-        case JPGB_RGBA: return launch_fast_ct<JPGB_RGBA>(p, grid, block, smem, stream);
-        case JPGB_BGR: return launch_fast_ct<JPGB_BGR>(p, grid, block, smem, stream);
-        case JPGB_BGRA: return launch_fast_ct<JPGB_BGRA>(p, grid, block, smem, stream);
-        case JPGB_CMYK_AS_YCCK: return launch_fast_ct<JPGB_CMYK_AS_YCCK>(p, grid, block, smem, stream);
+        case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, block, smem, stream);
+        case JPGB_RGB: return launch_fast_ct<JPGB_RGB>(p, block, smem, stream);
+        case JPGB_RGBA: return launch_fast_ct<JPGB_RGBA>(p, block, smem, stream);
+        case JPGB_BGR: return launch_fast_ct<JPGB_BGR>(p, block, smem, stream);
+        case JPGB_BGRA: return launch_fast_ct<JPGB_BGRA>(p, block, smem, stream);
+        case JPGB_CMYK_AS_YCCK: return launch_fast_ct<JPGB_CMYK_AS_YCCK>(p, block, smem, stream);
         default: break;
         }
     }
