@@ -69,7 +69,7 @@ struct jpgb_encoder {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
+    DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
         scan_tmp, hist;
     PinnedBuf h_small, h_hist, h_tables;
     bool timing = false;
@@ -226,6 +226,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 
     // ---- symbol sizing and the two prefix sums ----
     CK(enc->nbits.reserve(n_visits * 4), "alloc nbits");
+    CK(enc->slots.reserve(n_visits * 4 * kSlotWords), "alloc code slots");
     CK(enc->bitpos.reserve((n_visits + 1) * 8), "alloc bitpos");
     CK(enc->seglen.reserve(n_segs * 4), "alloc seglen");
     CK(enc->segpos.reserve((n_segs + 1) * 8), "alloc segpos");
@@ -238,6 +239,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     b.huff = enc->huff.as<uint32_t>();
     b.huff_per_image = optimized ? 1 : 0;
     b.nbits = enc->nbits.as<uint32_t>();
+    b.slots = enc->slots.as<uint32_t>();
     b.bitpos = enc->bitpos.as<unsigned long long>();
     b.seglen = enc->seglen.as<uint32_t>();
     b.segpos = enc->segpos.as<unsigned long long>();
@@ -388,7 +390,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->bitpos, &e->seglen, &e->segpos,
+    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
                       &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();

@@ -14,12 +14,12 @@
 // next scan's SOS) and its data bytes, then EOI. `raw_mask` flags header/marker bytes so that the
 // stuffing pass leaves their 0xFF alone.
 //
-//   symbol_size_kernel   visit -> number of bits                (DC differencing, run/size symbols)
+//   encode_visits_kernel visit -> its code bits (in a slot) and their count (DC differencing, run/size symbols)
 //   [exclusive scan]     bit position of every visit
 //   segment_len_kernel   segment -> lead + ceil(bits/8) + tail bytes
 //   [exclusive scan]     byte position of every segment in the unstuffed stream
 //   segment_lead_kernel  writes headers / RSTn / SOS / EOI, sets raw_mask
-//   emit_bits_kernel     visit -> code bits OR-ed into the unstuffed stream, pad bits at segment end
+//   place_bits_kernel    slot bits shifted into the unstuffed stream, pad bits at segment end
 //   count_ff_kernel      chunk -> number of data 0xFF bytes
 //   [exclusive scan]
 //   stuff_scatter_kernel copies every byte to its final place, inserting 0x00 after data 0xFF
@@ -120,54 +120,39 @@ __device__ __forceinline__ void value_code(int v, int &size, uint32_t &bits) {
     bits = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << size) - 1u);
 }
 
-// Bit sink. COUNT mode adds lengths; EMIT mode packs MSB-first into 32-bit big-endian words of the
-// unstuffed stream. The first and the last word of a visit are shared with its neighbours and are
-// merged with atomicOr (the stream is zero-initialised); interior words are owned and stored.
-template <bool EMIT>
+// Bit sink of one visit. Codes are packed MSB-first into 32-bit words; word j of visit g goes to
+// slots[j * stride + g] (word-major: the lanes of a warp, which flush word j at about the same time,
+// write one contiguous line). The visit is coded exactly once; where its bits belong in the stream is
+// decided later, from the prefix sum of `total`, by place_bits_kernel.
 struct BitSink {
     unsigned total = 0;
     unsigned long long acc = 0;
     int n = 0;
-    uint32_t *word = nullptr;
-    bool first = true;
+    uint32_t *slot;
+    unsigned long long stride;
 
-    __device__ __forceinline__ void begin(uint8_t *stream, unsigned long long bitpos) {
-        if (EMIT) {
-            word = reinterpret_cast<uint32_t *>(stream) + (bitpos >> 5);
-            n = (int)(bitpos & 31);
-        }
-    }
+    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long stride_, unsigned long long g)
+        : slot(slots + g), stride(stride_) {}
     __device__ __forceinline__ void put(uint32_t code, int len) {
-        if (!EMIT) {
-            total += len;
-            return;
-        }
+        total += len;
         acc = (acc << len) | code;
         n += len;
         if (n >= 32) {
-            const uint32_t w = (uint32_t)(acc >> (n - 32));
-            const uint32_t be = __byte_perm(w, 0, 0x0123);
-            if (first) atomicOr(word, be);
-            else *word = be;
-            first = false;
-            ++word;
+            *slot = (uint32_t)(acc >> (n - 32));
+            slot += stride;
             n -= 32;
         }
     }
     __device__ __forceinline__ void finish() {
-        if (EMIT && n > 0) {
-            const uint32_t w = (uint32_t)(acc << (32 - n));
-            atomicOr(word, __byte_perm(w, 0, 0x0123));
-        }
+        if (n > 0) *slot = (uint32_t)(acc << (32 - n)); // left-aligned tail
     }
 };
 
 // write_dc + write_ac_block restricted to [ss, se] for one visit (writer.rs:342-388).
 // A symbol without a code has lookup 0: only the value bits are written (release-build behaviour
 // of the reference).
-template <bool EMIT>
 __device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *__restrict__ dc_tab,
-                                           const uint32_t *__restrict__ ac_tab, BitSink<EMIT> &sink) {
+                                           const uint32_t *__restrict__ ac_tab, BitSink &sink) {
     const uint4 *src = reinterpret_cast<const uint4 *>(vi.blk);
     int run = 0;
     const int first_ac = vi.ss == 0 ? 1 : vi.ss;
@@ -207,7 +192,7 @@ __device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *
             }
         }
     }
-    if (run > 0) {
+    if (run > 0) { // the band ends in zeros: EOB (writer.rs:383-385)
         const uint32_t e = __ldg(ac_tab);
         sink.put(e & 0xFFFFu, (int)(e >> 16));
     }
@@ -217,14 +202,15 @@ __device__ __forceinline__ const uint32_t *huff_for(const EntropyBuffers &b, uns
     return b.huff + (b.huff_per_image ? img * kHuffWordsPerImage : 0) + (size_t)(tbl * 2 + cls) * 256;
 }
 
-__global__ void __launch_bounds__(256) symbol_size_kernel(const EntropyBuffers b, unsigned long long n_visits) {
+__global__ void __launch_bounds__(256) encode_visits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_visits) return;
     const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
     const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
-    BitSink<false> sink;
-    code_visit<false>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    BitSink sink(b.slots, n_visits, g);
+    code_visit(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    sink.finish();
     b.nbits[g] = sink.total;
 }
 
@@ -303,24 +289,73 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
     }
 }
 
-__global__ void __launch_bounds__(256) emit_bits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
+// Moves the already coded bits of visit g from its slot to their place in the unstuffed stream:
+// a bit-granular copy (funnel shift by the start position modulo 32). The first and the last stream
+// word of a visit are shared with its neighbours and are merged with atomicOr (the stream is
+// zero-initialised); words in between are owned and stored. The last visit of a segment also
+// writes the pad bits of finalize_bit_buffer (writer.rs:138-145: ones up to the byte boundary).
+__global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_visits) return;
     const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
-    const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
-    const unsigned long long seg = img * P.segs_per_image + vi.seg_local;
-    const unsigned long long data_byte = b.segpos[seg] + lead_len(b, P, img, vi.scan, vi.seg_in_scan);
-    const unsigned long long rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + vi.first_visit_of_seg];
+    unsigned nb = b.nbits[g];
+    // segment bookkeeping only (no coefficient access)
+    const int k = find_scan_by_visit(P, v);
+    const DevScan &S = P.scans[k];
+    const unsigned long long rel = v - S.visit_base;
+    const unsigned unit = (unsigned)(rel / S.bpu), slot_in_unit = (unsigned)(rel - (unsigned long long)unit * S.bpu);
+    const unsigned R = (unsigned)P.restart;
+    const unsigned seg_in_scan = R ? unit / R : 0;
+    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && (unit + 1) % R == 0));
+    if (nb == 0 && !last_of_seg) return;
+    const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
+    const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
+    const unsigned long long data_byte = b.segpos[seg] + lead_len(b, P, img, k, seg_in_scan);
+    const unsigned long long rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + first_visit];
     const unsigned long long bitpos = data_byte * 8 + rel_bits;
-    BitSink<true> sink;
-    sink.begin(b.ustream, bitpos);
-    code_visit<true>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
-    if (vi.last_of_seg) { // finalize_bit_buffer, writer.rs:138-145: pad to the byte boundary with ones
-        const unsigned end_bits = (unsigned)((rel_bits + b.nbits[g]) & 7);
-        if (end_bits) sink.put((1u << (8 - end_bits)) - 1u, 8 - (int)end_bits);
+
+    uint32_t *dst = reinterpret_cast<uint32_t *>(b.ustream) + (bitpos >> 5);
+    const unsigned sh = (unsigned)(bitpos & 31);
+    const unsigned n_words = (nb + 31) >> 5;
+    const uint32_t *src = b.slots + g;
+    unsigned pad = 0;
+    if (last_of_seg) {
+        const unsigned end_bits = (unsigned)((rel_bits + nb) & 7);
+        pad = end_bits ? 8 - end_bits : 0;
     }
-    sink.finish();
+    uint32_t carry = 0; // bits still to be written into the current destination word (left-aligned)
+    bool first = true;
+    for (unsigned j = 0; j < n_words; ++j) {
+        uint32_t w = src[(unsigned long long)j * n_visits];
+        const unsigned have = (j + 1 == n_words) ? nb - 32 * j : 32u; // valid bits in w (left-aligned)
+        if (j + 1 == n_words && pad) { // append the pad ones behind the last code bits when they fit in this word
+            if (have + pad <= 32) {
+                w |= ((1u << pad) - 1u) << (32 - have - pad);
+                pad = 0;
+            }
+        }
+        const uint32_t out = carry | (sh ? (w >> sh) : w);
+        const bool full = sh + have >= 32; // this destination word is completed by w
+        const uint32_t be = __byte_perm(out, 0, 0x0123);
+        if (first || !full) atomicOr(dst, be);
+        else *dst = be;
+        first = false;
+        if (full) {
+            ++dst;
+            carry = sh ? (w << (32 - sh)) : 0u;
+            if (j + 1 == n_words) { // bits of the last word that spilled into the next destination word
+                const unsigned spill = sh + have - 32;
+                if (spill) atomicOr(dst, __byte_perm(carry, 0, 0x0123));
+            }
+        }
+    }
+    if (pad) { // pad bits that did not fit next to the last code word (or a visit without bits)
+        const unsigned long long p = bitpos + nb;
+        uint32_t *d2 = reinterpret_cast<uint32_t *>(b.ustream) + (p >> 5);
+        const unsigned s2 = (unsigned)(p & 31); // pad never crosses a byte, hence never a word
+        atomicOr(d2, __byte_perm(((1u << pad) - 1u) << (32 - s2 - pad), 0, 0x0123));
+    }
 }
 
 // ---- 0xFF stuffing (writer.rs:156-167) as count / scan / scatter ---------------------------------
@@ -357,7 +392,10 @@ __global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b, u
 }
 
 __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers b, unsigned long long bytes) {
+    // The chunk's output is first laid out in shared memory at the same offset modulo 16 as its place
+    // in `out`, then copied with aligned 128-bit stores (single bytes only at the two ends).
     __shared__ unsigned warp_excl[9];
+    __shared__ __align__(16) uint8_t stage[2 * kStuffChunk + 32];
     const unsigned long long base = (unsigned long long)blockIdx.x * kStuffChunk + (unsigned long long)threadIdx.x * 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 d = make_uint4(0, 0, 0, 0);
@@ -382,14 +420,30 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
         for (int i = 1; i <= 8; ++i) warp_excl[i] += warp_excl[i - 1];
     }
     __syncthreads();
-    if (valid == 0) return;
-    unsigned long long o = base + b.ffpos[blockIdx.x] + warp_excl[warp] + (inc - cnt);
-    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+    const unsigned long long chunk_base = (unsigned long long)blockIdx.x * kStuffChunk;
+    const unsigned long long out0 = chunk_base + b.ffpos[blockIdx.x]; // first output byte of this chunk
+    const unsigned pad = (unsigned)(out0 & 15);
+    const unsigned chunk_in = bytes - chunk_base < kStuffChunk ? (unsigned)(bytes - chunk_base) : (unsigned)kStuffChunk;
+    const unsigned total = chunk_in + warp_excl[8];
+    if (valid) {
+        unsigned o = pad + threadIdx.x * 16 + warp_excl[warp] + (inc - cnt);
+        const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        if ((unsigned)i < valid) {
-            b.out[o++] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
-            if (m & (1u << i)) b.out[o++] = 0x00;
+        for (int i = 0; i < 16; ++i) {
+            if ((unsigned)i < valid) {
+                stage[o++] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+                if (m & (1u << i)) stage[o++] = 0x00;
+            }
+        }
+    }
+    __syncthreads();
+    uint8_t *dst = b.out + (out0 - pad); // 16-byte aligned (b.out comes from cudaMalloc)
+    const unsigned end = pad + total;
+    for (unsigned o = threadIdx.x * 16; o < end; o += 256 * 16) {
+        if (o >= pad && o + 16 <= end) {
+            *reinterpret_cast<uint4 *>(dst + o) = *reinterpret_cast<const uint4 *>(stage + o);
+        } else {
+            for (unsigned k = (o < pad ? pad : o); k < o + 16 && k < end; ++k) dst[k] = stage[k];
         }
     }
 }
@@ -502,7 +556,7 @@ cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hp, const int16
 
 cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long nv = hp.visits_per_image * n;
-    symbol_size_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+    encode_visits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
     return cudaGetLastError();
 }
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
@@ -521,7 +575,7 @@ cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uin
 }
 cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long nv = hp.visits_per_image * n;
-    emit_bits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+    place_bits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
     return cudaGetLastError();
 }
 cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {

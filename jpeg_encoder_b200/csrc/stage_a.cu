@@ -15,6 +15,7 @@
 // shuffles, no shared-memory round trip, no divergence. Each lane then writes its 128-byte block.
 //
 // All arithmetic is 32-bit integer; tensor cores are not used (the DCT must be bit-exact).
+#include <cstdlib>
 #include <utility>
 
 #include "kernels.h"
@@ -413,8 +414,8 @@ __device__ __forceinline__ void stage_tile(const StageAParams &p, const TileCoor
 // HS x VS = sampling factor of the full-resolution components (luma, K); the others are 1x1.
 // Persistent: each CTA walks tiles t = blockIdx.x, + gridDim.x, ... with two shared-memory buffers,
 // so the cp.async traffic of tile i+1 is in flight while the warps transform tile i.
-template <int CT, int HS, int VS>
-__global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
+template <int CT, int HS, int VS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;                         // are there subsampled (1x1) components?
@@ -430,11 +431,11 @@ __global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_const
     cp_async_commit();
     for (unsigned it = 0; t < n_tiles; t += gridDim.x, ++it) {
         uint8_t *tile = smem + (it & 1) * tile_bytes;
+        cp_async_wait<0>(); // this thread's share of tile `t` has landed ...
+        __syncthreads();    // ... and so has everybody else's; also: every warp has finished tile t - grid
         const unsigned nt = t + gridDim.x;
         if (nt < n_tiles) stage_tile<BPP, VS>(p, tile_coord(p, nt), smem + ((it + 1) & 1) * tile_bytes);
-        cp_async_commit();
-        cp_async_wait<1>(); // everything but the group just committed has landed: tile `t` is complete
-        __syncthreads();
+        cp_async_commit();  // tile t + grid streams in while tile t is transformed: one barrier per tile
 
         const TileCoord tc = tile_coord(p, t);
         for (int task = warp; task < n_tasks; task += n_warps) {
@@ -476,19 +477,17 @@ __global__ void __launch_bounds__(256, 2) stage_a_fast_kernel(const __grid_const
             if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
             else quantize_store256<1>(p, v, dst);
         }
-        __syncthreads(); // every warp is done with this buffer before the next iteration refills it
     }
     cp_async_wait<0>();
 }
 
-template <int CT, int HS, int VS>
-cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
-    static int ctas_per_sm = 0, n_sms = 0;
+template <int CT, int HS, int VS, int NT, int MINB>
+cudaError_t launch_fast_v(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
     const size_t smem = 2 * tile_bytes;
-    auto kernel = stage_a_fast_kernel<CT, HS, VS>;
+    auto kernel = stage_a_fast_kernel<CT, HS, VS, NT, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int dev = 0;
+    int dev = 0, n_sms = 0, ctas_per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, (int)block.x, smem);
@@ -499,6 +498,20 @@ cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cu
     if (grid > n_tiles) grid = n_tiles;
     kernel<<<(unsigned)grid, block, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int CT, int HS, int VS>
+cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
+    if (block.x <= 192) {
+        if constexpr (CT == JPGB_RGB && HS == 2 && VS == 2) { // experiment hook: occupancy variants
+            static const char *v = std::getenv("JPGB_STAGE_A_MINB");
+            if (v && v[0] == '3') return launch_fast_v<CT, HS, VS, 192, 3>(p, block, tile_bytes, stream);
+            if (v && v[0] == '4') return launch_fast_v<CT, HS, VS, 192, 4>(p, block, tile_bytes, stream);
+        }
+        // measured on B200 (C3): 2 CTAs x 128 registers beat 3 x 96 and 4 x 80 (spills, less ILP)
+        return launch_fast_v<CT, HS, VS, 192, 2>(p, block, tile_bytes, stream);
+    }
+    return launch_fast_v<CT, HS, VS, 256, 2>(p, block, tile_bytes, stream);
 }
 
 template <int CT>
