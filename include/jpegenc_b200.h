@@ -114,6 +114,40 @@ int jpgb_encode_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *co
 int jpgb_encode_batch_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels,
                              size_t image_stride, uint32_t n, const void **d_files, uint64_t *offsets);
 
+/* ---- one very large image split into strips of whole MCU rows (BASELINE config 5) ---------------
+ * No reference equivalent: the crate encodes an image on one thread. A strip boundary must fall on
+ * a restart boundary of *every* scan (src/encoder.rs:748-757, 833-839: the DC predictors reset and
+ * the bit stream is byte aligned there), so strips need restart_interval > 0, first_row a multiple
+ * of 8*Vmax, and in every scan (first unit of the strip) % restart_interval == 0.
+ * Each strip is encoded on its own GPU; the final file is, scan by scan, the concatenation of the
+ * strips' pieces: strip 0's piece of scan 0 starts with the file header (SOI .. first SOS), its
+ * piece of scan k > 0 with that scan's SOS; every other piece starts with the RSTn marker that
+ * precedes its first segment; the last strip's last piece ends with EOI. */
+typedef struct jpgb_strip {
+    uint32_t strip_index, n_strips;
+    uint16_t first_row;   /* first pixel row of the strip in the whole image */
+    uint16_t rows;        /* pixel rows in the strip */
+    uint16_t full_height; /* height of the whole image (goes into SOF) */
+} jpgb_strip;
+
+/* number of scans the settings produce (1 interleaved, ncomp sequential, ncomp * scans progressive) */
+int jpgb_scan_count(const jpgb_params *p, uint32_t *n_scans);
+
+/* Largest number of equal-as-possible strips <= max_strips the image can be cut into, and their
+ * (first_row, rows). Returns JPGB_ERR_BAD_PARAMS when the settings do not allow strips at all. */
+int jpgb_plan_strips(const jpgb_params *p, uint32_t max_strips, jpgb_strip *strips, uint32_t *n_strips);
+
+/* Encode one strip. `p->height` is the whole image's height; `d_pixels` (device) points at the
+ * strip's first row. On return *d_bytes is device memory owned by the context holding the strip's
+ * pieces back to back and piece_offsets[0..n_scans] (host) delimits piece k as
+ * [piece_offsets[k], piece_offsets[k+1]). Optimized Huffman tables are not available with strips
+ * (they need the whole image's histogram). */
+int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                             const void **d_bytes, uint64_t *piece_offsets);
+
+/* Copy `n` bytes of context-owned (or any) device memory to host memory; synchronous on the context's stream. */
+int jpgb_download(jpgb_encoder *enc, const void *d_src, size_t n, void *host_dst);
+
 /* ---- stage-level entry points (parity tests and roofline timing) ------------------------------ */
 
 /* Block-grid geometry of the coefficient buffer for `p`: per component the MCU-padded grid

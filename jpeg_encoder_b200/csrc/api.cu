@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,8 +71,8 @@ struct jpgb_encoder {
     bool own_stream = false;
     std::string err;
     DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
-        scan_tmp, hist;
-    PinnedBuf h_small, h_hist, h_tables;
+        scan_tmp, hist, piece_off;
+    PinnedBuf h_small, h_hist, h_tables, h_pieces;
     bool timing = false;
     cudaEvent_t ev[JPGB_N_STAGES + 1][2] = {};
     bool ev_used[JPGB_N_STAGES] = {};
@@ -145,7 +146,7 @@ int validate_and_plan(jpgb_encoder *enc, const jpgb_params *p, size_t len_each, 
 // The whole device pipeline for `n` device-resident images. On success the files lie back to back
 // in enc->out and `offsets` (host, n + 1) delimits them.
 int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, size_t image_stride, uint32_t n,
-                  std::vector<uint64_t> &offsets) {
+                  std::vector<uint64_t> &offsets, std::vector<uint64_t> *piece_offsets = nullptr) {
     cudaStream_t st = enc->stream;
     DevPlan hp;
     plan.fill_device_plan(hp);
@@ -300,8 +301,17 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         CK(launch_file_offsets(b, hp, n, ubytes, st), "file offsets launch");
         enc->launches += 2;
         CK(cudaMemcpyAsync(enc->h_small.p, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
+        if (piece_offsets) { // strip mode: where each scan's bytes start
+            const size_t np = plan.scans.size() + 1;
+            CK(enc->piece_off.reserve(np * 8), "alloc piece offsets");
+            CK(enc->h_pieces.reserve(np * 8), "alloc piece offsets (host)");
+            CK(launch_scan_offsets(b, hp, ubytes, enc->piece_off.as<unsigned long long>(), st), "scan offsets launch");
+            enc->launches += 1;
+            CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
+        }
     }
     CK(cudaStreamSynchronize(st), "final sync");
+    if (piece_offsets) piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
     offsets.assign(enc->h_small.as<uint64_t>(), enc->h_small.as<uint64_t>() + n + 1);
     enc->out_total = total;
     if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
@@ -391,11 +401,12 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
-                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist};
+                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
     e->h_hist.release();
     e->h_tables.release();
+    e->h_pieces.release();
     for (int i = 0; i < JPGB_N_STAGES; ++i)
         for (int k = 0; k < 2; ++k)
             if (e->ev[i][k]) cudaEventDestroy(e->ev[i][k]);
@@ -448,6 +459,79 @@ int jpgb_encode_batch_device(jpgb_encoder *enc, const jpgb_params *p, const void
     timing_end(enc);
     std::memcpy(offsets, off.data(), (size_t)(n + 1) * 8);
     *d_files = enc->out.p;
+    return JPGB_OK;
+}
+
+int jpgb_scan_count(const jpgb_params *p, uint32_t *n_scans) {
+    if (!p || !n_scans) return JPGB_ERR_BAD_PARAMS;
+    Plan plan;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return rc;
+    *n_scans = (uint32_t)plan.scans.size();
+    return JPGB_OK;
+}
+
+int jpgb_plan_strips(const jpgb_params *p, uint32_t max_strips, jpgb_strip *strips, uint32_t *n_strips) {
+    if (!p || !strips || !n_strips || max_strips == 0) return JPGB_ERR_BAD_PARAMS;
+    Plan plan;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return rc;
+    const uint32_t R = p->restart_interval;
+    if (R == 0 || p->optimize_huffman) return JPGB_ERR_BAD_PARAMS;
+    auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
+    // a strip may start at MCU row r only if r * (units per MCU row) is a multiple of R in every scan
+    uint64_t step = 1;
+    for (const Scan &s : plan.scans) {
+        const uint64_t upr = s.comp < 0 ? plan.mcu_cols : (uint64_t)plan.comps[s.comp].v * plan.true_w[s.comp];
+        const uint64_t need = R / gcd(R, upr);
+        step = step / gcd(step, need) * need;
+    }
+    const uint64_t groups = (plan.mcu_rows + step - 1) / step; // groups of `step` MCU rows (the last may be short)
+    uint32_t n = (uint32_t)std::min<uint64_t>(max_strips, groups);
+    if (n == 0) n = 1;
+    const uint32_t rows_per_mcu = 8 * plan.vmax;
+    uint64_t g0 = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t g1 = groups * (i + 1) / n;
+        const uint64_t r0 = g0 * step * rows_per_mcu, r1 = std::min<uint64_t>(g1 * step * rows_per_mcu, p->height);
+        strips[i].strip_index = i;
+        strips[i].n_strips = n;
+        strips[i].first_row = (uint16_t)r0;
+        strips[i].rows = (uint16_t)(r1 - r0);
+        strips[i].full_height = p->height;
+        g0 = g1;
+    }
+    *n_strips = n;
+    return JPGB_OK;
+}
+
+int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                             const void **d_bytes, uint64_t *piece_offsets) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!p || !strip || !d_pixels || !d_bytes || !piece_offsets) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    if (p->color_type > JPGB_YCCK) return fail(enc, JPGB_ERR_BAD_PARAMS, "bad color_type");
+    Plan plan;
+    const int rc = plan.build(*p, strip);
+    if (rc != JPGB_OK) return fail(enc, rc, "settings or strip geometry do not allow strip encoding (needs restart intervals aligned in every scan)");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    timing_begin(enc);
+    std::vector<uint64_t> off, pieces;
+    const size_t stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
+    const int rc2 = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), stride, 1, off, &pieces);
+    if (rc2 != JPGB_OK) return rc2;
+    timing_end(enc);
+    std::memcpy(piece_offsets, pieces.data(), pieces.size() * 8);
+    *d_bytes = enc->out.p;
+    return JPGB_OK;
+}
+
+int jpgb_download(jpgb_encoder *enc, const void *d_src, size_t n, void *host_dst) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (n == 0) return JPGB_OK;
+    if (!d_src || !host_dst) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    CK(cudaMemcpyAsync(host_dst, d_src, n, cudaMemcpyDeviceToHost, enc->stream), "download");
+    CK(cudaStreamSynchronize(enc->stream), "download sync");
     return JPGB_OK;
 }
 

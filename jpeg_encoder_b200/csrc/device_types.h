@@ -43,6 +43,7 @@ struct DevScan {
     unsigned long long visit_base;
     unsigned seg_base, n_segs;
     unsigned sos_off, sos_len;  // into DevPlan::blob
+    unsigned rst_base;          // restart segments of this scan that lie before this strip (0 for a whole image)
 };
 
 struct DevPlan {
@@ -50,6 +51,7 @@ struct DevPlan {
     unsigned mcu_cols;
     unsigned long long visits_per_image, blocks_per_image;
     unsigned segs_per_image;
+    int has_eoi;            // 0 for every strip but the last
     int8_t slot_comp[kMaxSlots], slot_v[kMaxSlots], slot_h[kMaxSlots];
     int comp_h[4], comp_v[4], comp_tbl[4];
     unsigned comp_pw[4], comp_tw[4];   // padded / true blocks per row

@@ -151,14 +151,20 @@ struct BitSink {
 // write_dc + write_ac_block restricted to [ss, se] for one visit (writer.rs:342-388).
 // A symbol without a code has lookup 0: only the value bits are written (release-build behaviour
 // of the reference).
+// FULL: the scan covers the whole block (ss = 0, se = 63: baseline and sequential scans), so the
+// per-coefficient band checks vanish. Groups of 8 and pairs of coefficients that are all zero only
+// extend the current zero run.
+template <bool FULL>
 __device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *__restrict__ dc_tab,
                                            const uint32_t *__restrict__ ac_tab, BitSink &sink) {
     const uint4 *src = reinterpret_cast<const uint4 *>(vi.blk);
     int run = 0;
-    const int first_ac = vi.ss == 0 ? 1 : vi.ss;
-    const int w_lo = vi.se == 0 ? 0 : first_ac >> 3, w_hi = vi.se >> 3;
-    if (vi.ss == 0) {
-        const int dc = vi.blk[0];
+    const int ss = FULL ? 0 : vi.ss, se = FULL ? 63 : vi.se;
+    const int first_ac = ss == 0 ? 1 : ss;
+    const int w_lo = se == 0 ? 0 : first_ac >> 3, w_hi = se >> 3;
+    uint4 q = __ldg(src + w_lo);
+    if (ss == 0) {
+        const int dc = (int)(int16_t)(q.x & 0xFFFFu); // w_lo == 0 whenever ss == 0
         const int prev = vi.pred ? (int)vi.pred[0] : 0;
         const int diff = (int)(int16_t)(dc - prev);
         int size;
@@ -167,30 +173,41 @@ __device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *
         const uint32_t h = __ldg(dc_tab + size);
         sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
     }
-    if (vi.se == 0) return;
+    if (se == 0) return;
+    const uint32_t zrl = __ldg(ac_tab + 0xF0);
     for (int w = w_lo; w <= w_hi; ++w) {
-        const uint4 q = __ldg(src + w);
-        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+        const uint4 nxt = w < w_hi ? __ldg(src + w + 1) : q; // prefetch the next group
+        const bool edge = w == 0 || (!FULL && (w == w_lo || w == w_hi));
+        if (!edge && (q.x | q.y | q.z | q.w) == 0) {
+            run += 8;
+        } else {
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = w * 8 + j;
-            const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
-            if (k < first_ac || k > vi.se) continue;
-            if (c == 0) {
-                ++run;
-            } else {
-                if (run > 15) {
-                    const uint32_t z = __ldg(ac_tab + 0xF0);
-                    for (; run > 15; run -= 16) sink.put(z & 0xFFFFu, (int)(z >> 16));
+            for (int i = 0; i < 4; ++i) {
+                if (!edge && words[i] == 0) {
+                    run += 2;
+                    continue;
                 }
-                int size;
-                uint32_t bits;
-                value_code(c, size, bits);
-                const uint32_t h = __ldg(ac_tab + ((run << 4) | size));
-                sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
-                run = 0;
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int k = w * 8 + 2 * i + hlf;
+                    if (FULL ? k == 0 : (k < first_ac || k > se)) continue;
+                    const int c = (int)(int16_t)(words[i] >> (hlf * 16));
+                    if (c == 0) {
+                        ++run;
+                    } else {
+                        for (; run > 15; run -= 16) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));
+                        int size;
+                        uint32_t bits;
+                        value_code(c, size, bits);
+                        const uint32_t h = __ldg(ac_tab + ((run << 4) | size));
+                        sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
+                        run = 0;
+                    }
+                }
             }
         }
+        q = nxt;
     }
     if (run > 0) { // the band ends in zeros: EOB (writer.rs:383-385)
         const uint32_t e = __ldg(ac_tab);
@@ -209,7 +226,8 @@ __global__ void __launch_bounds__(256) encode_visits_kernel(const EntropyBuffers
     const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
     const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
     BitSink sink(b.slots, n_visits, g);
-    code_visit(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    if (vi.ss == 0 && vi.se == 63) code_visit<true>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
+    else code_visit<false>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
     sink.finish();
     b.nbits[g] = sink.total;
 }
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(256) encode_visits_kernel(const EntropyBuffers
 // (writer.rs:424-452) or RSTn (encoder.rs:748-752: marker index = restarts % 8).
 __device__ __forceinline__ unsigned lead_len(const EntropyBuffers &b, const DevPlan &P, unsigned long long img, int k,
                                              unsigned seg_in_scan) {
-    if (seg_in_scan > 0) return 2;
+    if (P.scans[k].rst_base + seg_in_scan > 0) return 2; // RSTn (for a strip: also before its first segment)
     if (k > 0) return P.scans[k].sos_len;
     return b.hdr_len[b.huff_per_image ? img : 0];
 }
@@ -238,7 +256,7 @@ __global__ void __launch_bounds__(256) segment_len_kernel(const EntropyBuffers b
     const unsigned long long vn = (i + 1 < S.n_segs) ? vf + span : S.visit_base + (unsigned long long)S.n_units * S.bpu;
     const unsigned long long vb = img * P.visits_per_image;
     const unsigned long long bits = b.bitpos[vb + vn] - b.bitpos[vb + vf];
-    const unsigned tail = s == P.segs_per_image - 1 ? 2u : 0u; // EOI, encoder.rs:564
+    const unsigned tail = (s == P.segs_per_image - 1 && P.has_eoi) ? 2u : 0u; // EOI, encoder.rs:564
     b.seglen[g] = lead_len(b, P, img, k, i) + (unsigned)((bits + 7) >> 3) + tail;
 }
 
@@ -269,10 +287,10 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
     const DevScan &S = P.scans[k];
     const unsigned i = s - S.seg_base;
     const unsigned long long pos = b.segpos[g];
-    if (i > 0) {
+    if (S.rst_base + i > 0) {
         if (lane == 0) {
             put_raw(b, pos, 0xFF);
-            put_raw(b, pos + 1, (uint8_t)(0xD0 + ((i - 1) & 7)));
+            put_raw(b, pos + 1, (uint8_t)(0xD0 + ((S.rst_base + i - 1) & 7)));
         }
     } else if (k > 0) {
         for (unsigned j = lane; j < S.sos_len; j += 32) put_raw(b, pos + j, P.blob[S.sos_off + j]);
@@ -282,7 +300,7 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
         const uint8_t *src = b.hdr + h * b.hdr_stride;
         for (unsigned j = lane; j < n; j += 32) put_raw(b, pos + j, src[j]);
     }
-    if (s == P.segs_per_image - 1 && lane == 0) {
+    if (s == P.segs_per_image - 1 && P.has_eoi && lane == 0) {
         const unsigned long long end = b.segpos[g + 1];
         put_raw(b, end - 2, 0xFF);
         put_raw(b, end - 1, 0xD9);
@@ -465,6 +483,21 @@ __global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers 
     if (lane == 0) b.file_off[img] = pos + b.ffpos[chunk] + ff;
 }
 
+// final byte offset of the first segment of every scan of image 0 (+ the end): the pieces of a strip
+__global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers b, unsigned long long bytes, unsigned long long *offs) {
+    const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const DevPlan &P = *b.plan;
+    if (k > (unsigned)P.n_scans) return;
+    const unsigned long long pos = k == (unsigned)P.n_scans ? bytes : b.segpos[P.scans[k].seg_base];
+    const unsigned long long chunk = pos / kStuffChunk;
+    unsigned ff = 0;
+    for (unsigned long long i = chunk * kStuffChunk + lane; i < pos; i += 32)
+        if (b.ustream[i] == 0xFF && !((b.raw_mask[i >> 5] >> (i & 31)) & 1u)) ++ff;
+    ff = __reduce_add_sync(0xffffffffu, ff);
+    if (lane == 0) offs[k] = pos + b.ffpos[chunk] + ff;
+}
+
 // ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
 // One thread per block of each component's *true* grid. DC category of the chained difference with
 // no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL
@@ -584,6 +617,10 @@ cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t bytes, cudaStream_
 }
 cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {
     stuff_scatter_kernel<<<grid_for(bytes, kStuffChunk), 256, 0, s>>>(b, bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hp, uint64_t bytes, unsigned long long *offs, cudaStream_t s) {
+    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, bytes, offs);
     return cudaGetLastError();
 }
 cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, uint64_t bytes, cudaStream_t s) {

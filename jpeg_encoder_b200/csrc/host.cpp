@@ -235,8 +235,13 @@ void default_huffman_tables(HuffTable huff[2][2]) {
 }
 
 // ---- plan ---------------------------------------------------------------------------------------
-int Plan::build(const jpgb_params &params) {
+int Plan::build(const jpgb_params &params, const jpgb_strip *st) {
     p = params;
+    is_strip = st != nullptr;
+    if (st) {
+        strip = *st;
+        p.height = st->rows; // geometry below is the strip's; the SOF carries strip.full_height
+    }
     if (p.color_type > JPGB_YCCK) return JPGB_ERR_BAD_PARAMS;
     const int sh = (p.sampling >> 4) & 0x07, sv = p.sampling & 0x0f; // get_sampling_factors, encoder.rs:173-176
     auto pow2 = [](int f) { return f == 1 || f == 2 || f == 4; };
@@ -344,6 +349,18 @@ int Plan::build(const jpgb_params &params) {
             for (int c = 0; c < ncomp; ++c) add_scan(c, start, end - 1);
         }
     }
+    if (is_strip) {
+        if (!p.restart_interval || p.optimize_huffman) return JPGB_ERR_BAD_PARAMS;
+        if (strip.n_strips == 0 || strip.strip_index >= strip.n_strips || strip.rows == 0) return JPGB_ERR_BAD_PARAMS;
+        if (strip.first_row % (8 * vmax) != 0 || (uint32_t)strip.first_row + strip.rows > strip.full_height) return JPGB_ERR_BAD_PARAMS;
+        if (strip.strip_index + 1 < strip.n_strips && strip.rows % (8 * vmax) != 0) return JPGB_ERR_BAD_PARAMS;
+        const uint32_t mcu_row0 = strip.first_row / (8 * vmax);
+        for (Scan &s : scans) {
+            const uint64_t first_unit = s.comp < 0 ? (uint64_t)mcu_row0 * mcu_cols : (uint64_t)mcu_row0 * comps[s.comp].v * true_w[s.comp];
+            if (first_unit % p.restart_interval != 0) return JPGB_ERR_BAD_PARAMS;
+            s.rst_base = (uint32_t)(first_unit / p.restart_interval);
+        }
+    }
     visits_per_image = 0;
     segs_per_image = 0;
     for (Scan &s : scans) {
@@ -379,7 +396,7 @@ void Plan::frame_header(const HuffTable huff[2][2], std::vector<uint8_t> &o) con
     put_marker(o, p.progressive_scans ? 0xC2 : 0xC0); // writer.rs:390-422
     put16(o, 2 + 1 + 2 + 2 + 1 + ncomp * 3);
     o.push_back(8);
-    put16(o, p.height);
+    put16(o, is_strip ? strip.full_height : p.height);
     put16(o, p.width);
     o.push_back((uint8_t)ncomp);
     for (int c = 0; c < ncomp; ++c) {
@@ -419,6 +436,7 @@ void Plan::fill_device_plan(DevPlan &d) const {
     d.visits_per_image = visits_per_image;
     d.blocks_per_image = blocks_per_image;
     d.segs_per_image = segs_per_image;
+    d.has_eoi = !is_strip || strip.strip_index + 1 == strip.n_strips;
     int n = 0;
     for (int c = 0; c < ncomp; ++c) {
         d.comp_h[c] = comps[c].h;
@@ -448,6 +466,7 @@ void Plan::fill_device_plan(DevPlan &d) const {
         ds.visit_base = s.visit_base;
         ds.seg_base = s.seg_base;
         ds.n_segs = s.n_segs;
+        ds.rst_base = s.rst_base;
         ds.sos_off = blob;
         ds.sos_len = 0;
         if (k > 0) { // scan 0's SOS travels with the per-image file header

@@ -43,6 +43,7 @@ struct Scan {
     uint32_t n_units, blocks_per_unit;
     uint64_t visit_base;   // first block visit of this scan inside one image
     uint32_t seg_base, n_segs;
+    uint32_t rst_base = 0; // restart segments of this scan before this strip
     std::vector<uint8_t> sos; // SOS segment bytes (marker included)
 };
 
@@ -63,7 +64,10 @@ struct Plan {
     uint32_t segs_per_image;
     std::vector<uint8_t> prefix; // SOI, APP0, [APP14], user APPn  (src/encoder.rs:536-554)
 
-    int build(const jpgb_params &params); // returns JPGB_* code
+    // strip mode (strip != nullptr): geometry of the strip, header of the whole image
+    bool is_strip = false;
+    jpgb_strip strip{};
+    int build(const jpgb_params &params, const jpgb_strip *strip = nullptr); // returns JPGB_* code
     // SOF, DQT x2, DHT x2|4, [DRI] (Encoder::write_frame_header, src/encoder.rs:633-667)
     void frame_header(const HuffTable huff[2][2], std::vector<uint8_t> &out) const;
     void fill_device_plan(DevPlan &d) const;

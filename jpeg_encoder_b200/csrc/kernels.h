@@ -53,6 +53,8 @@ cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hplan, 
 cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
 cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
+cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint64_t ustream_bytes, unsigned long long *offs,
+                                cudaStream_t stream);
 cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, uint64_t ustream_bytes,
                                 cudaStream_t stream);
 

@@ -136,6 +136,11 @@ class _CoefLayout(C.Structure):
                 ("blocks_per_image", C.c_uint64)]
 
 
+class _Strip(C.Structure):
+    _fields_ = [("strip_index", C.c_uint32), ("n_strips", C.c_uint32), ("first_row", C.c_uint16), ("rows", C.c_uint16),
+                ("full_height", C.c_uint16)]
+
+
 N_STAGES = 7
 STAGE_NAMES = ("colour_dct_quant", "histogram_tables", "symbol_sizes_scans", "emit_bits", "stuff_scatter", "h2d", "d2h")
 
@@ -167,6 +172,10 @@ def load_library():
                                     C.POINTER(u8p), C.POINTER(C.c_size_t)]
     l.jpgb_encode_batch_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32,
                                            C.POINTER(vp), C.POINTER(C.c_uint64)]
+    l.jpgb_scan_count.argtypes = [C.POINTER(_Params), C.POINTER(C.c_uint32)]
+    l.jpgb_plan_strips.argtypes = [C.POINTER(_Params), C.c_uint32, C.POINTER(_Strip), C.POINTER(C.c_uint32)]
+    l.jpgb_encode_strip_device.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Strip), vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    l.jpgb_download.argtypes = [vp, vp, C.c_size_t, vp]
     l.jpgb_coef_layout_for.argtypes = [C.POINTER(_Params), C.POINTER(_CoefLayout)]
     l.jpgb_stage_a_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32, vp]
     l.jpgb_encoder_set_timing.argtypes = [vp, C.c_int]
@@ -201,6 +210,14 @@ class Device:
             self.close()
         except Exception:
             pass
+
+    def download(self, d_ptr, nbytes):
+        """Copy nbytes of device memory (e.g. the files of encode_batch_device) into a bytes object."""
+        buf = C.create_string_buffer(nbytes)
+        rc = self.lib.jpgb_download(self.handle, C.c_void_p(d_ptr), nbytes, buf)
+        if rc != 0:
+            raise EncodingError(rc, self.last_error())
+        return buf.raw
 
     def last_error(self):
         return self.lib.jpgb_last_error(self.handle).decode()
@@ -426,6 +443,39 @@ class Encoder:
         if rc != 0:
             self._raise(rc)
         return d_files.value, list(offs)
+
+    # -- one large image cut into restart-aligned strips (BASELINE config 5) --
+    def scan_count(self, width, height, color_type):
+        p = self._params(width, height, ColorType(color_type))
+        n = C.c_uint32()
+        rc = load_library().jpgb_scan_count(C.byref(p), C.byref(n))
+        if rc != 0:
+            raise EncodingError(rc)
+        return n.value
+
+    def plan_strips(self, width, height, color_type, max_strips):
+        """[(first_row, rows)] for at most max_strips strips whose boundaries are restart boundaries of
+        every scan. Raises EncodingError(BadParams) if the settings do not allow strips."""
+        p = self._params(width, height, ColorType(color_type))
+        arr = (_Strip * max_strips)()
+        n = C.c_uint32()
+        rc = load_library().jpgb_plan_strips(C.byref(p), max_strips, arr, C.byref(n))
+        if rc != 0:
+            raise EncodingError(rc, "strips need a restart interval that divides every scan's units per MCU-row group")
+        return [(arr[i].first_row, arr[i].rows) for i in range(n.value)]
+
+    def encode_strip_device(self, d_pixels, strip_index, n_strips, first_row, rows, width, full_height, color_type):
+        """Encode one strip (device pointer at its first row). Returns (device pointer, piece offsets[n_scans+1])."""
+        dev = self._dev()
+        p = self._params(width, full_height, ColorType(color_type))
+        st = _Strip(strip_index, n_strips, first_row, rows, full_height)
+        n_scans = self.scan_count(width, full_height, color_type)
+        d_bytes = C.c_void_p()
+        offs = (C.c_uint64 * (n_scans + 1))()
+        rc = dev.lib.jpgb_encode_strip_device(dev.handle, C.byref(p), C.byref(st), C.c_void_p(d_pixels), C.byref(d_bytes), offs)
+        if rc != 0:
+            self._raise(rc)
+        return d_bytes.value, list(offs)
 
     def coef_layout(self, width, height, color_type):
         p = self._params(width, height, ColorType(color_type))

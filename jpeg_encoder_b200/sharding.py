@@ -1,0 +1,63 @@
+"""How the encode path is spread over the GPUs of one box.
+
+* Batches shard by image: rank r owns images [lo, hi) -- no data-path collective at all.
+* One very large image shards by strips of whole MCU rows whose boundaries are restart boundaries
+  of every scan. Each rank encodes its strip; the only exchange is the gather of the strips'
+  per-scan byte pieces to rank 0 (sizes first, then one variable-length send per rank over
+  NCCL/NVLink), where they are concatenated scan-major.
+
+The exchange functions work on whatever device the tensors live on: NCCL with CUDA tensors on the
+B200 box, gloo with CPU tensors in the world_size-2 CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(n_images, world, rank):
+    """Contiguous, balanced image range of `rank`: sizes differ by at most one."""
+    base, extra = divmod(n_images, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def assemble_pieces(pieces_by_strip):
+    """pieces_by_strip[s][k] = bytes of scan k produced by strip s. The file is scan-major:
+    for each scan, strips in order (strip 0's piece carries the header / SOS, the last strip's last
+    piece the EOI)."""
+    n_scans = len(pieces_by_strip[0])
+    out = bytearray()
+    for k in range(n_scans):
+        for strip in pieces_by_strip:
+            out += strip[k]
+    return bytes(out)
+
+
+def split_pieces(buf, offsets):
+    return [bytes(buf[offsets[k]:offsets[k + 1]]) for k in range(len(offsets) - 1)]
+
+
+def gather_strip_pieces(local_bytes, piece_offsets, rank, world, device, group=None):
+    """local_bytes: uint8 tensor on `device` holding this rank's pieces back to back.
+    Returns on rank 0 the assembled uint8 tensor of the whole file (scan-major), on other ranks None.
+    Communication: one all_gather of the (n_scans + 1) offsets, then one send per non-zero rank."""
+    n = len(piece_offsets)
+    mine = torch.tensor(piece_offsets, dtype=torch.int64, device=device)
+    table = [torch.empty(n, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(table, mine, group=group)
+    table = [t.cpu().tolist() for t in table]
+    if rank == 0:
+        bufs = [local_bytes]
+        reqs = []
+        for r in range(1, world):
+            b = torch.empty(table[r][-1], dtype=torch.uint8, device=device)
+            bufs.append(b)
+            reqs.append(dist.irecv(b, src=r, group=group))
+        for q in reqs:
+            q.wait()
+        parts = []
+        for k in range(n - 1):
+            for r in range(world):
+                parts.append(bufs[r][table[r][k]:table[r][k + 1]])
+        return torch.cat(parts)
+    dist.send(local_bytes[:piece_offsets[-1]].contiguous(), dst=0, group=group)
+    return None

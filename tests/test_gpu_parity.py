@@ -251,3 +251,37 @@ def test_config4_small_scale_gray_and_ycck_custom_tables():
 def test_config5_progressive_420_medium():
     _same("rgb", 2048, 2048, dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048),
           img=images.photo_like(2048, 2048, 3, seed=6))
+
+
+# ---- one image cut into restart-aligned strips (BASELINE config 5 mechanics, on one GPU) ---------
+def _encode_by_strips(img, w, h, color, cfg, max_strips):
+    import torch
+    import jpeg_encoder_b200 as je
+    from jpeg_encoder_b200 import sharding
+    enc = make_encoder(cfg)
+    ct = CT[color][1]
+    strips = enc.plan_strips(w, h, ct, max_strips)
+    dev = je.default_device(0)
+    flat = np.ascontiguousarray(img).reshape(h, -1)
+    pieces = []
+    for i, (r0, rows) in enumerate(strips):
+        d_px = torch.from_numpy(flat[r0:r0 + rows].copy()).cuda()
+        torch.cuda.synchronize()
+        d_bytes, offs = enc.encode_strip_device(d_px.data_ptr(), i, len(strips), r0, rows, w, h, ct)
+        pieces.append(sharding.split_pieces(dev.download(d_bytes, offs[-1]), offs))
+    return sharding.assemble_pieces(pieces), len(strips)
+
+
+@pytest.mark.parametrize("name,color,w,h,cfg,max_strips", [
+    ("progressive_420", "rgb", 512, 400, dict(quality=85, sampling=(2, 2), progressive_scans=4, restart_interval=32), 4),
+    ("progressive_420_odd", "rgb", 509, 397, dict(quality=85, sampling=(2, 2), progressive_scans=4, restart_interval=64), 8),
+    ("interleaved_restart", "rgb", 640, 360, dict(quality=90, sampling=(2, 2), restart_interval=20), 6),
+    ("sequential_4_1", "rgb", 512, 256, dict(quality=75, sampling=(4, 1), restart_interval=16), 4),
+    ("luma", "luma", 384, 512, dict(quality=95, restart_interval=48), 8),
+    ("ycck_progressive", "cmyk_as_ycck", 256, 256, dict(quality=90, sampling=(1, 1), progressive_scans=3, restart_interval=32), 4),
+])
+def test_strips_concatenate_to_the_whole_image(name, color, w, h, cfg, max_strips):
+    img = _img(color, w, h, seed=21)
+    got, n = _encode_by_strips(img, w, h, color, cfg, max_strips)
+    assert n > 1, "test geometry must actually split"
+    assert got == oracle_encode(img, w, h, color, cfg)

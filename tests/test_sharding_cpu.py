@@ -1,0 +1,98 @@
+"""Host-side logic of the multi-GPU paths on CPU: batch sharding, strip planning through the C ABI
+(no kernels), scan-major assembly, and the world_size-2 gather over gloo."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import jpeg_encoder_b200 as je
+from jpeg_encoder_b200 import sharding
+
+
+def test_shard_batch_covers_everything():
+    for n in (1, 7, 8, 1024, 1025):
+        for world in (1, 2, 4, 8):
+            spans = [sharding.shard_batch(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _enc(restart, sampling=je.SamplingFactor.F_2_2, progressive=None, optimize=False):
+    e = je.Encoder(90)
+    e.set_sampling_factor(sampling)
+    e.set_restart_interval(restart)
+    if progressive:
+        e.set_progressive_scans(progressive)
+    e.set_optimized_huffman_tables(optimize)
+    return e
+
+
+def test_plan_strips_config5_geometry():
+    """16384^2 RGB progressive 4:2:0, restart 2048: 8 strips of 128 MCU rows."""
+    strips = _enc(2048, progressive=4).plan_strips(16384, 16384, je.ColorType.Rgb, 8)
+    assert strips == [(i * 2048, 2048) for i in range(8)]
+    assert _enc(2048, progressive=4).scan_count(16384, 16384, je.ColorType.Rgb) == 12
+
+
+def test_plan_strips_alignment_rules():
+    # luma 240 blocks per row, chroma 120: restart 64 needs groups of 8 MCU rows (8*120 % 64 == 0)
+    strips = _enc(64, progressive=4).plan_strips(1920, 1080, je.ColorType.Rgb, 8)
+    assert all(r % (8 * 16) == 0 for r, _ in strips)
+    assert sum(n for _, n in strips) == 1080 and strips[0][0] == 0
+    # interleaved: units are MCUs (120 per row): restart 7 only aligns every 7 MCU rows
+    strips = _enc(7).plan_strips(1920, 1080, je.ColorType.Rgb, 4)
+    assert all(r % (7 * 16) == 0 for r, _ in strips)
+    assert sum(n for _, n in strips) == 1080
+    # never more strips than aligned groups; a single group gives one strip
+    assert len(_enc(65535).plan_strips(640, 480, je.ColorType.Rgb, 8)) == 1
+    with pytest.raises(je.EncodingError):
+        _enc(0).plan_strips(1920, 1080, je.ColorType.Rgb, 8)  # no restart interval: replicas only
+    with pytest.raises(je.EncodingError):
+        _enc(64, optimize=True).plan_strips(1920, 1080, je.ColorType.Rgb, 8)  # needs a global histogram
+
+
+def test_assemble_is_scan_major():
+    a = [b"H0", b"S1a", b"S2a"]
+    b = [b"r0", b"r1", b"r2E"]
+    assert sharding.assemble_pieces([a, b]) == b"H0r0S1ar1S2ar2E"
+    assert sharding.split_pieces(b"abcdef", [0, 2, 2, 6]) == [b"ab", b"", b"cdef"]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank r owns pieces of 3 scans with rank-dependent sizes
+    pieces = [bytes([10 * rank + k]) * (3 + 2 * rank + k) for k in range(3)]
+    offs = [0]
+    for pc in pieces:
+        offs.append(offs[-1] + len(pc))
+    buf = torch.tensor(list(b"".join(pieces)), dtype=torch.uint8)
+    out = sharding.gather_strip_pieces(buf, offs, rank, world, torch.device("cpu"))
+    if rank == 0:
+        q.put(bytes(out.tolist()))
+    lo, hi = sharding.shard_batch(11, world, rank)
+    t = torch.tensor([hi - lo])
+    dist.all_reduce(t)
+    assert int(t) == 11
+    dist.destroy_process_group()
+
+
+def test_gather_strip_pieces_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    exp = sharding.assemble_pieces([[bytes([10 * r + k]) * (3 + 2 * r + k) for k in range(3)] for r in range(world)])
+    assert got == exp
