@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- megapixels/s of the JPEG encode hot path on N B200s (BASELINE.json `metric`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4a|c4b] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4a|c4b|c5] [--impl reference]
 
 A step = one pass of the whole encode path (colour -> DCT -> quant -> entropy -> stuffed JFIF bytes)
 over one batch of synthetic frames. Default workload: BASELINE config 3, a batch of 1920x1080 RGB
@@ -39,6 +39,9 @@ WORKLOADS = {
             "1 x 8192x8192 grayscale q95 custom tables (BASELINE config 4a)"),
     "c4b": (8192, 8192, "cmyk_as_ycck", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
             "1 x 8192x8192 CMYK->YCCK q95 4:4:4 custom tables (BASELINE config 4b)"),
+    "c5": (16384, 16384, "rgb", dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048), 1,
+           "1 x 16384x16384 RGB progressive (4 scans per component, spectral selection) 4:2:0, restart 2048, "
+           "split by restart-aligned strips across the GPUs, pieces gathered to rank 0 (BASELINE config 5)"),
 }
 BPP = {"luma": 1, "rgb": 3, "cmyk_as_ycck": 4}
 DISTINCT = 16  # distinct synthetic frames; the batch repeats them (inputs stay >> L2: 6.2 MB per frame)
@@ -173,6 +176,8 @@ def run_product(args):
 
     width, height, color, cfg, def_batch, desc = WORKLOADS[args.workload]
     cfg = resolve_cfg(cfg)
+    if args.workload == "c5":
+        return run_strips(args, rank, world, local, dev_t)
     batch = args.batch or def_batch
     bpp = BPP[color]
     img_bytes = width * height * bpp
@@ -337,6 +342,163 @@ def run_product(args):
         dist.destroy_process_group()
 
 
+# ---- one very large image, strips across the GPUs (BASELINE config 5) ---------------------------
+def run_strips(args, rank, world, local, dev_t):
+    import torch
+    import torch.distributed as dist
+    import images
+    import jpeg_encoder_b200 as je
+    from cases import CT, make_encoder, oracle_encode
+    from jpeg_encoder_b200 import sharding
+
+    width, height, color, cfg, _, desc = WORKLOADS[args.workload]
+    if args.size:
+        width = height = args.size
+    ct = CT[color][1]
+    bpp = BPP[color]
+    stream = torch.cuda.current_stream()
+    device = je.Device(local, cuda_stream=stream.cuda_stream)
+    enc = make_encoder(cfg, device)
+    strips = enc.plan_strips(width, height, ct, world)
+    if len(strips) != world:
+        raise SystemExit("bench.py: image cannot be cut into %d restart-aligned strips (got %d)" % (world, len(strips)))
+    r0, rows = strips[rank]
+    seed = 7
+    d_strip = images.synth_frame_torch(width, height, bpp, seed=seed, row0=r0, rows=rows, device=dev_t).reshape(-1)
+    torch.cuda.synchronize()
+
+    def encode_once():
+        d_bytes, offs = enc.encode_strip_device(d_strip.data_ptr(), rank, world, r0, rows, width, height, ct)
+        return d_bytes, offs
+
+    def step(gather=True):
+        d_bytes, offs = encode_once()
+        launches = device.last_launch_count()
+        tm = device.last_timing()
+        out = None
+        if world > 1 and gather:
+            # wrap the context-owned device buffer (no copy) and gather the pieces to rank 0 over NCCL
+            local_bytes = _as_tensor(d_bytes, offs[-1], dev_t)
+            out = sharding.gather_strip_pieces(local_bytes, offs, rank, world, dev_t)
+        elif gather:
+            out = _as_tensor(d_bytes, offs[-1], dev_t)
+        return out, launches, tm
+
+    # parity gate (un-timed): the assembled file must equal the oracle's for the whole image
+    out, _, _ = step()
+    if rank == 0:
+        got = bytes(out.cpu().numpy().tobytes())
+        if not args.skip_parity:
+            full = torch.cat([images.synth_frame_torch(width, height, bpp, seed=seed, row0=a, rows=b, device=dev_t).cpu()
+                              for a, b in strips]).numpy()
+            want = oracle_encode(full, width, height, color, cfg)
+            if got != want:
+                raise SystemExit("bench.py: assembled strips differ from the oracle (%d vs %d bytes)" % (len(got), len(want)))
+            del full
+        out_bytes = len(got)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    device.set_timing(True)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms, launches = {}, 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        _, l, tm = step()
+        launches += l
+        for k, v in (tm or {}).items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    mp = width * height / 1e6
+    value = mp / (ms_per_step / 1e3)
+
+    # end to end: pinned host strip -> device -> encode -> gather -> host file on rank 0
+    h_strip = d_strip.cpu().pin_memory()
+    d_stage = torch.empty_like(d_strip)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        d_stage.copy_(h_strip, non_blocking=True)
+        d_bytes, offs = enc.encode_strip_device(d_stage.data_ptr(), rank, world, r0, rows, width, height, ct)
+        if world > 1:
+            o = sharding.gather_strip_pieces(_as_tensor(d_bytes, offs[-1], dev_t), offs, rank, world, dev_t)
+        else:
+            o = _as_tensor(d_bytes, offs[-1], dev_t)
+        if rank == 0:
+            d2h = o.cpu().numel()
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = (float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if os.path.exists(peaks_path) \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    lay = enc.coef_layout(width, rows, ct)
+    a_bytes = width * rows * bpp + 128 * int(lay.blocks_per_image)
+    a_ms = stage_ms.get("colour_dct_quant", 0.0) / args.steps
+    achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else None
+    line = {
+        "metric": "megapixels/sec encoded, byte-identical to the reference restatement",
+        "value": value, "unit": "megapixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8 in / i32 arithmetic / i16 coefficients", "data": "synthetic",
+        "config": {"workload": desc, "workload_id": args.workload, "width": width, "height": height,
+                   "strips": [[int(a), int(b)] for a, b in strips], "settings": cfg, "bytes_out": out_bytes,
+                   "l2": "strip input %.0f MB per GPU, larger than L2" % (width * rows * bpp / 1e6),
+                   "collective": "one all_gather of piece sizes + one NCCL send per non-zero rank (gather to rank 0)"},
+        "clocks": clocks,
+        "e2e": {"value": mp * e2e_steps / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": width * height * bpp,
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "api": "pinned host strip -> jpgb_encode_strip_device -> NCCL gather -> host file on rank 0"},
+        "gpu_launches": launches,
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "roofline": {"bound": "hbm", "kernel": "stage_a_fast_kernel (colour+decimate+fDCT+quant), rank 0's strip", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes, "ms_per_launch": a_ms},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _as_tensor(d_ptr, nbytes, dev_t):
+    """Zero-copy torch view of context-owned device memory (valid until the next call on the context)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(d_ptr), False), "version": 3}
+    return torch.as_tensor(h, device=dev_t)
+
+
 # ---- the reference arm: the CPU restatement on the host cores -------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -386,6 +548,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--size", type=int, default=0, help="c5 only: square image size override (testing)")
+    ap.add_argument("--skip-parity", action="store_true", help="c5 only: skip the whole-image oracle comparison")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

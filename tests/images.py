@@ -93,3 +93,28 @@ def synth_frame(width, height, channels=3, seed=0):
         planes.append(np.clip((a * 5 + b * 3) // 8 + t + n - 12, 0, 255).astype(np.uint8))
     img = np.stack(planes, axis=-1)
     return img[..., 0] if channels == 1 else img
+
+
+def synth_frame_torch(width, height, channels=3, seed=0, row0=0, rows=None, device="cuda"):
+    """synth_frame evaluated with torch integer ops on `device`, for rows [row0, row0 + rows): the
+    same values as the numpy version (used for the 16384^2 workload, generated strip by strip)."""
+    import torch
+    rows = height - row0 if rows is None else rows
+    y = torch.arange(row0, row0 + rows, dtype=torch.int64, device=device)[:, None]
+    x = torch.arange(width, dtype=torch.int64, device=device)[None, :]
+
+    def tri(t, period):
+        t = t % period
+        return (t - period // 2).abs() * 510 // period
+
+    planes = []
+    for c in range(channels):
+        a = tri(x * (3 + c) + y * (2 + seed % 5) + seed * 131 + c * 977, 2048 + 256 * c)
+        b = tri(x * (1 + (seed >> 2) % 3) - y * (4 + c) + seed * 29, 1536 + 128 * (seed % 7))
+        t = tri(x * 37 + y * 53 + c * 11, 64) >> 3
+        hsh = (x * 0x9E3779B1 + y * 0x85EBCA77 + (seed * 4 + c) * 0xC2B2AE3D) & 0xFFFFFFFF
+        hsh = (hsh ^ (hsh >> 15)) * 0x2C1B3C6D & 0xFFFFFFFF
+        n = ((hsh >> 13) & 7) - 4
+        planes.append(((a * 5 + b * 3) // 8 + t + n - 12).clamp(0, 255).to(torch.uint8))
+    img = torch.stack(planes, dim=-1)
+    return img[..., 0].contiguous() if channels == 1 else img.contiguous()

@@ -106,3 +106,17 @@ def test_setters_mirror_reference():
         assert je.SamplingFactor.from_factors(h, v).get_sampling_factors() == (h, v)
     assert je.SamplingFactor.R_4_2_0.get_sampling_factors() == (2, 2)
     assert je.SamplingFactor.from_factors(4, 4) is None
+
+
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """include/jpeg_encoder.hpp (the compiled-language mirror of the reference API) builds against the C ABI."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "mirror_smoke")
+    pkg = os.path.join(ROOT, "jpeg_encoder_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mirror_smoke.cpp"),
+                           "-o", exe, "-L" + pkg, "-ljpegenc_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert "EncodingError 8" in r.stdout  # JPGB_ERR_CUDA: no fallback

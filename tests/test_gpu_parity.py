@@ -285,3 +285,15 @@ def test_strips_concatenate_to_the_whole_image(name, color, w, h, cfg, max_strip
     got, n = _encode_by_strips(img, w, h, color, cfg, max_strips)
     assert n > 1, "test geometry must actually split"
     assert got == oracle_encode(img, w, h, color, cfg)
+
+
+def test_cpp_mirror_on_gpu(tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "jpeg_encoder_b200")
+    exe = str(tmp_path / "mirror_smoke")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "mirror_smoke.cpp"),
+                           "-o", exe, "-L" + pkg, "-ljpegenc_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "tail ok" in r.stdout, r.stdout + r.stderr
