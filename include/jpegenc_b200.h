@@ -106,6 +106,12 @@ int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *
 int jpgb_encode_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels,
                       size_t len_each, uint32_t n, uint8_t **outs, size_t *out_lens);
 
+/* Same, without the per-file copies: the n files are left back to back in pinned host memory owned by
+ * the context (*files), file i at [offsets[i], offsets[i+1]) (host array of n + 1). Valid until the
+ * next call on this context. Uploads, encoding and downloads of consecutive chunks overlap. */
+int jpgb_encode_batch_pinned(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels,
+                             size_t len_each, uint32_t n, const uint8_t **files, uint64_t *offsets);
+
 /* Device-resident batch: `d_pixels` is device memory holding n images `image_stride` bytes apart.
  * The n files are written back to back into device memory owned by the context; on return
  * *d_files points at it and offsets[0..n] (host array of n+1) delimits file i as

@@ -71,8 +71,11 @@ struct jpgb_encoder {
     bool own_stream = false;
     std::string err;
     DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
-        scan_tmp, hist, piece_off;
-    PinnedBuf h_small, h_hist, h_tables, h_pieces;
+        scan_tmp, hist, piece_off, out2, pixels2;
+    PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out;
+    int out_slot = 0; // which of out / out2 the next encode_device writes
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_enc[2] = {};
     bool timing = false;
     cudaEvent_t ev[JPGB_N_STAGES + 1][2] = {};
     bool ev_used[JPGB_N_STAGES] = {};
@@ -293,8 +296,9 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     }
     CK(cudaStreamSynchronize(st), "stuffing sync");
     const uint64_t total = ubytes + *enc->h_small.as<uint64_t>();
-    CK(enc->out.reserve(total + 64), "alloc output");
-    b.out = enc->out.as<uint8_t>();
+    DevBuf &outb = enc->out_slot ? enc->out2 : enc->out;
+    CK(outb.reserve(total + 64), "alloc output");
+    b.out = outb.as<uint8_t>();
     {
         StageTimer t(enc, 4);
         CK(launch_stuff_scatter(b, ubytes, st), "scatter launch");
@@ -318,42 +322,114 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     return JPGB_OK;
 }
 
+// Host pixels -> host files for n images, pipelined in chunks over three streams: while chunk c is
+// encoded on the context's stream, chunk c+1 is uploaded (s_h2d) and the files of chunk c-1 are
+// downloaded (s_d2h) into one pinned buffer owned by the context. PCIe moves 3 B/pixel in and the
+// files out; the device pipeline itself is ~10x faster, so the copies set the pace.
+// On success file i is h_out[offsets[i] .. offsets[i+1]).
+int encode_host_pipelined(jpgb_encoder *enc, const Plan &plan, const uint8_t *const *pixels, uint32_t n,
+                          std::vector<uint64_t> &offsets) {
+    const size_t img_bytes = (size_t)plan.p.width * plan.p.height * plan.bpp;
+    const size_t stride = (img_bytes + 255) & ~(size_t)255;
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, (96u << 20) / stride); // ~96 MB of pixels per chunk
+    if (plan.p.optimize_huffman) chunk = std::min<uint32_t>(chunk, 16);  // one histogram launch per image
+    chunk = std::min(chunk, n);
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    CK(enc->pixels.reserve(stride * chunk), "alloc pixels");
+    if (n_chunks > 1) CK(enc->pixels2.reserve(stride * chunk), "alloc pixels");
+    CK(enc->h_out.reserve(std::max<size_t>(img_bytes * n / 3, 1 << 20)), "alloc pinned output");
+    offsets.assign(1, 0);
+    cudaStream_t st = enc->stream;
+
+    auto upload = [&](uint32_t c) -> cudaError_t {
+        DevBuf &px = (c & 1) ? enc->pixels2 : enc->pixels;
+        const uint32_t lo = c * chunk, hi = std::min(n, lo + chunk);
+        if (c >= 2) { // the buffer was last read by the encode of chunk c-2
+            cudaError_t e = cudaStreamWaitEvent(enc->s_h2d, enc->ev_enc[c & 1], 0);
+            if (e != cudaSuccess) return e;
+        }
+        for (uint32_t i = lo; i < hi; ++i) {
+            cudaError_t e = cudaMemcpyAsync(px.as<uint8_t>() + stride * (i - lo), pixels[i], img_bytes, cudaMemcpyHostToDevice, enc->s_h2d);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaEventRecord(enc->ev_in[c & 1], enc->s_h2d);
+    };
+
+    {
+        StageTimer t(enc, 5);
+        CK(upload(0), "upload pixels");
+    }
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t lo = c * chunk, hi = std::min(n, lo + chunk), cn = hi - lo;
+        if (c + 1 < n_chunks) CK(upload(c + 1), "upload pixels");
+        DevBuf &px = (c & 1) ? enc->pixels2 : enc->pixels;
+        CK(cudaStreamWaitEvent(st, enc->ev_in[c & 1], 0), "wait upload");
+        if (c >= 2) CK(cudaStreamWaitEvent(st, enc->ev_out[c & 1], 0), "wait download"); // out slot reused
+        enc->out_slot = (int)(c & 1);
+        std::vector<uint64_t> off;
+        const uint32_t launches_before = enc->launches;
+        const int rc = encode_device(enc, plan, px.as<uint8_t>(), stride, cn, off);
+        enc->out_slot = 0;
+        if (rc != JPGB_OK) return rc;
+        (void)launches_before;
+        CK(cudaEventRecord(enc->ev_enc[c & 1], st), "record encode");
+        const uint64_t bytes = off[cn];
+        if (total + bytes > enc->h_out.cap) { // grow the pinned buffer, keeping what is already there
+            CK(cudaStreamSynchronize(enc->s_d2h), "download sync");
+            PinnedBuf bigger;
+            CK(bigger.reserve((total + bytes) * 2), "grow pinned output");
+            std::memcpy(bigger.p, enc->h_out.p, total);
+            enc->h_out.release();
+            enc->h_out = bigger;
+        }
+        DevBuf &ob = (c & 1) ? enc->out2 : enc->out;
+        // encode_device has synchronised the context's stream: the files are complete in `ob`
+        CK(cudaMemcpyAsync(enc->h_out.as<uint8_t>() + total, ob.p, bytes, cudaMemcpyDeviceToHost, enc->s_d2h), "download files");
+        CK(cudaEventRecord(enc->ev_out[c & 1], enc->s_d2h), "record download");
+        for (uint32_t i = 0; i < cn; ++i) offsets.push_back(total + off[i + 1]);
+        total += bytes;
+    }
+    {
+        StageTimer t(enc, 6);
+        CK(cudaStreamSynchronize(enc->s_d2h), "download sync");
+    }
+    return JPGB_OK;
+}
+
 int encode_host_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels, size_t len_each, uint32_t n,
-                      uint8_t **outs, size_t *out_lens) {
+                      uint8_t **outs, size_t *out_lens, const uint8_t **pinned_base, uint64_t *pinned_offsets) {
     if (!enc) return JPGB_ERR_BAD_PARAMS;
-    if (!pixels || !outs || !out_lens || n == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
-    for (uint32_t i = 0; i < n; ++i) outs[i] = nullptr, out_lens[i] = 0;
+    const bool pinned_api = pinned_base != nullptr;
+    if (!pixels || n == 0 || (pinned_api ? !pinned_offsets : (!outs || !out_lens))) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    if (!pinned_api)
+        for (uint32_t i = 0; i < n; ++i) outs[i] = nullptr, out_lens[i] = 0;
     Plan plan;
     int rc = validate_and_plan(enc, p, len_each, plan);
     if (rc != JPGB_OK) return rc;
     CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    const bool was_timing = enc->timing;
+    enc->timing = false; // per-stage events are per encode_device call; the pipelined path runs several
     timing_begin(enc);
-    const size_t img_bytes = (size_t)plan.p.width * plan.p.height * plan.bpp;
-    const size_t stride = (img_bytes + 255) & ~(size_t)255;
-    CK(enc->pixels.reserve(stride * n), "alloc pixels");
-    {
-        StageTimer t(enc, 5);
-        for (uint32_t i = 0; i < n; ++i)
-            CK(cudaMemcpyAsync(enc->pixels.as<uint8_t>() + stride * i, pixels[i], img_bytes, cudaMemcpyHostToDevice, enc->stream), "upload pixels");
-    }
     std::vector<uint64_t> off;
-    rc = encode_device(enc, plan, enc->pixels.as<uint8_t>(), stride, n, off);
+    rc = encode_host_pipelined(enc, plan, pixels, n, off);
+    enc->timing = was_timing;
     if (rc != JPGB_OK) return rc;
-    {
-        StageTimer t(enc, 6);
-        for (uint32_t i = 0; i < n; ++i) {
-            const size_t sz = (size_t)(off[i + 1] - off[i]);
-            outs[i] = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
-            if (!outs[i]) {
-                for (uint32_t k = 0; k < i; ++k) std::free(outs[k]), outs[k] = nullptr;
-                return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
-            }
-            out_lens[i] = sz;
-            CK(cudaMemcpyAsync(outs[i], enc->out.as<uint8_t>() + off[i], sz, cudaMemcpyDeviceToHost, enc->stream), "download file");
-        }
+    if (pinned_api) {
+        *pinned_base = enc->h_out.as<uint8_t>();
+        std::memcpy(pinned_offsets, off.data(), (size_t)(n + 1) * 8);
+        return JPGB_OK;
     }
-    CK(cudaStreamSynchronize(enc->stream), "download sync");
-    timing_end(enc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const size_t sz = (size_t)(off[i + 1] - off[i]);
+        outs[i] = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
+        if (!outs[i]) {
+            for (uint32_t k = 0; k < i; ++k) std::free(outs[k]), outs[k] = nullptr;
+            return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
+        }
+        out_lens[i] = sz;
+        std::memcpy(outs[i], enc->h_out.as<uint8_t>() + off[i], sz);
+    }
     return JPGB_OK;
 }
 
@@ -392,6 +468,13 @@ int jpgb_encoder_create(int device, void *cuda_stream, jpgb_encoder **out) {
     }
     for (int i = 0; i < JPGB_N_STAGES; ++i)
         for (int k = 0; k < 2; ++k) cudaEventCreate(&e->ev[i][k]);
+    cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_enc[i], cudaEventDisableTiming);
+    }
     *out = e;
     return JPGB_OK;
 }
@@ -401,12 +484,20 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
-                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off};
+                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
     e->h_hist.release();
     e->h_tables.release();
     e->h_pieces.release();
+    e->h_out.release();
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+        if (e->ev_enc[i]) cudaEventDestroy(e->ev_enc[i]);
+    }
     for (int i = 0; i < JPGB_N_STAGES; ++i)
         for (int k = 0; k < 2; ++k)
             if (e->ev[i][k]) cudaEventDestroy(e->ev[i][k]);
@@ -421,7 +512,7 @@ int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, 
     *out = nullptr;
     *out_len = 0;
     const uint8_t *px[1] = {pixels};
-    return encode_host_batch(enc, p, px, len, 1, out, out_len);
+    return encode_host_batch(enc, p, px, len, 1, out, out_len, nullptr, nullptr);
 }
 
 void jpgb_free(void *buf) { std::free(buf); }
@@ -441,7 +532,13 @@ int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *
 
 int jpgb_encode_batch(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels, size_t len_each, uint32_t n,
                       uint8_t **outs, size_t *out_lens) {
-    return encode_host_batch(enc, p, pixels, len_each, n, outs, out_lens);
+    return encode_host_batch(enc, p, pixels, len_each, n, outs, out_lens, nullptr, nullptr);
+}
+
+int jpgb_encode_batch_pinned(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const *pixels, size_t len_each, uint32_t n,
+                             const uint8_t **files, uint64_t *offsets) {
+    if (!files) return JPGB_ERR_BAD_PARAMS;
+    return encode_host_batch(enc, p, pixels, len_each, n, nullptr, nullptr, files, offsets);
 }
 
 int jpgb_encode_batch_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_pixels, size_t image_stride, uint32_t n,

@@ -297,3 +297,20 @@ def test_cpp_mirror_on_gpu(tmp_path):
                            "-o", exe, "-L" + pkg, "-ljpegenc_b200", "-Wl,-rpath," + pkg])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "tail ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_pipelined_host_batch_many_chunks():
+    """Large enough to span several upload/encode/download chunks (two pixel and two output buffers in flight)."""
+    import ctypes as C
+    import jpeg_encoder_b200 as je
+    w, h, n = 1920, 1080, 40
+    frames = [images.synth_frame(w, h, 3, seed=s) for s in range(4)]
+    cfg = dict(quality=90, sampling=(2, 2))
+    want = [oracle_encode(f, w, h, "rgb", cfg) for f in frames]
+    enc = make_encoder(cfg)
+    outs = enc.encode_batch([frames[i % 4] for i in range(n)], w, h, je.ColorType.Rgb)
+    assert [o == want[i % 4] for i, o in enumerate(outs)] == [True] * n
+    cfg2 = dict(quality=80, sampling=(2, 2), optimize_huffman=True, restart_interval=100)
+    outs = make_encoder(cfg2).encode_batch([frames[i % 4] for i in range(20)], w, h, je.ColorType.Rgb)
+    want2 = [oracle_encode(f, w, h, "rgb", cfg2) for f in frames]
+    assert [o == want2[i % 4] for i, o in enumerate(outs)] == [True] * 20
