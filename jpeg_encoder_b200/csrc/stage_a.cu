@@ -52,6 +52,17 @@ __device__ __forceinline__ int sample(const uint8_t *px, int comp) {
     return formula_cr(r, g, b);
 }
 
+__device__ __forceinline__ int fma_add(int a, int b) { // a + b as IMAD
+    int r;
+    asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int fma_sub(int a, int b) { // a - b as IMAD
+    int r;
+    asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(r) : "r"(b), "r"(a));
+    return r;
+}
+
 // 1-D 8-point LL&M forward DCT (fdct.rs:116-171 for PASS 1, :178-237 for PASS 2).
 // PASS 1 takes *unshifted* samples 0..255: the -128 level shift (encoder.rs:1237) only moves the
 // DC term of the row by -128*8 << PASS1_BITS, every other output is a function of differences.
@@ -59,10 +70,12 @@ template <int PASS>
 __device__ __forceinline__ void dct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7) {
     constexpr int N = PASS == 1 ? 11 : 15; // CONST_BITS -/+ PASS1_BITS
     constexpr int RND = 1 << (N - 1);
-    const int tmp0 = d0 + d7, tmp7 = d0 - d7;
-    const int tmp1 = d1 + d6, tmp6 = d1 - d6;
-    const int tmp2 = d2 + d5, tmp5 = d2 - d5;
-    const int tmp3 = d3 + d4, tmp4 = d3 - d4;
+    // first butterflies on the FMA pipe (IMAD x*1+y): the ALU pipe carries the shifts, selects and
+    // remaining adds and is the busier of the two integer pipes (64 lanes/clk/SM each on B200)
+    const int tmp0 = fma_add(d7, d0), tmp7 = fma_sub(d0, d7);
+    const int tmp1 = fma_add(d6, d1), tmp6 = fma_sub(d1, d6);
+    const int tmp2 = fma_add(d5, d2), tmp5 = fma_sub(d2, d5);
+    const int tmp3 = fma_add(d4, d3), tmp4 = fma_sub(d3, d4);
     const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3;
     const int tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     if (PASS == 1) {
@@ -415,7 +428,14 @@ __device__ __forceinline__ void stage_tile(const StageAParams &p, const TileCoor
 // Persistent: each CTA walks tiles t = blockIdx.x, + gridDim.x, ... with two shared-memory buffers,
 // so the cp.async traffic of tile i+1 is in flight while the warps transform tile i.
 template <int CT, int HS, int VS, int NT, int MINB>
+__device__ __forceinline__ void stage_a_fast_body(const StageAParams &p);
+
+template <int CT, int HS, int VS, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
+    stage_a_fast_body<CT, HS, VS, NT, MINB>(p);
+}
+template <int CT, int HS, int VS, int NT, int MINB>
+__device__ __forceinline__ void stage_a_fast_body(const StageAParams &p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;                         // are there subsampled (1x1) components?
@@ -481,10 +501,147 @@ __global__ void __launch_bounds__(NT, MINB) stage_a_fast_kernel(const __grid_con
     cp_async_wait<0>();
 }
 
+// =================================================================================================
+// Warp-autonomous variant. Every warp owns a private shared-memory tile of 32 full-resolution blocks
+// (256 pixels) x one MCU row and walks warp tiles on its own: cp.async its pixel rows, wait with
+// __syncwarp only, then run its tasks -- the luma (and K) block rows and one chroma task in which
+// lanes 0..15 take Cb and lanes 16..31 Cr when chroma is horizontally decimated. No CTA barrier, no
+// role imbalance between warps; the other resident warps hide a warp's load latency.
+// =================================================================================================
+template <int CT, int HS, int VS>
+__global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_constant__ StageAParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int BPP = Fmt<CT>::BPP;
+    constexpr bool SUB = HS * VS > 1;
+    constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
+    constexpr int ROWS = 8 * VS;
+    constexpr int PITCH = 256 * BPP;            // 32 full-resolution blocks wide
+    constexpr int TILE_BYTES = PITCH * ROWS;
+    constexpr int MCUS = 32 / HS;               // MCUs per warp tile
+    // tasks of one warp tile: luma rows, [K rows], then chroma
+    constexpr int N_FULL = (NCOMP == 4 ? 2 : 1) * VS;
+    constexpr int N_CHROMA = NCOMP == 1 ? 0 : (SUB && HS == 2 ? 1 : 2); // Cb+Cr share a task when 16 blocks each
+    constexpr int N_TASKS = N_FULL + N_CHROMA;
+
+    const int lane = threadIdx.x & 31;
+    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
+    uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
+    const unsigned tiles_per_row = ((unsigned)p.mcu_cols + MCUS - 1) / MCUS;
+    const unsigned n_tiles = tiles_per_row * p.mcu_rows * p.n_images;
+    const size_t row_bytes = (size_t)p.width * BPP;
+
+    for (unsigned t = warp_global; t < n_tiles; t += n_warps_total) {
+        const unsigned tx = t % tiles_per_row, r = t / tiles_per_row;
+        const int mcu_y = (int)(r % (unsigned)p.mcu_rows), img = (int)(r / (unsigned)p.mcu_rows);
+        const int mcu_x0 = (int)tx * MCUS;
+        // ---- stage this warp's rows (cp.async, L2 only); edges replicated (Q4) ----
+        {
+            const int px0 = mcu_x0 * 8 * HS, py0 = mcu_y * ROWS;
+            const uint8_t *src = p.pixels + (size_t)img * p.image_stride;
+            const int valid_px = min(256, p.width - px0);
+            const int valid_bytes = valid_px * BPP;
+            const int needed_bytes = min(256, p.mcu_cols * 8 * HS - px0) * BPP;
+            __syncwarp(); // all lanes are done reading the previous tile
+#pragma unroll 4
+            for (int ry = 0; ry < ROWS; ++ry) {
+                const int sy = min(py0 + ry, p.height - 1);
+                const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+                uint8_t *dst = tile + ry * PITCH;
+                const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+                for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
+                    if (aligned && cb + 16 <= valid_bytes) {
+                        cp_async16(dst + cb, row + cb);
+                    } else {
+                        for (int b = 0; b < 16; ++b) {
+                            const int byte = cb + b;
+                            const int px = byte / BPP, ch = byte - px * BPP;
+                            dst[cb + b] = row[min(px, valid_px - 1) * BPP + ch];
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+        }
+        // ---- tasks ----
+#pragma unroll 1
+        for (int task = 0; task < N_TASKS; ++task) {
+            int comp, bv = 0, bxl = lane; // component, block row inside the MCU row, block column inside the tile
+            bool full = true;
+            if (task < N_FULL) {
+                comp = (NCOMP == 4 && task >= VS) ? 3 : 0;
+                bv = (NCOMP == 4 && task >= VS) ? task - VS : task;
+            } else if (N_CHROMA == 1) {
+                comp = lane < 16 ? 1 : 2;
+                bxl = lane & 15;
+                full = false;
+            } else {
+                comp = 1 + (task - N_FULL);
+                full = !SUB;
+            }
+            const int H = full ? HS : 1, V = full ? VS : 1;
+            const int bx = mcu_x0 * H + bxl;
+            if (bx >= p.comp_pw[comp]) continue;
+            const uint8_t *base = full ? tile + (bv * 8) * PITCH + bxl * 8 * BPP : tile + bxl * 8 * HS * BPP;
+
+            int v[64];
+            if constexpr (CT == JPGB_LUMA) {
+                load_block<CT, ROLE_RAW, 1, 1>(base, PITCH, v);
+            } else {
+                if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, PITCH, v);
+                else if (comp == 1) load_block<CT, ROLE_CB, SUB ? HS : 1, SUB ? VS : 1>(base, PITCH, v);
+                else if (NCOMP == 3 || comp == 2) load_block<CT, ROLE_CR, SUB ? HS : 1, SUB ? VS : 1>(base, PITCH, v);
+                else load_block<CT, ROLE_K, 1, 1>(base, PITCH, v);
+            }
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+                dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+                dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
+
+            const size_t blk = (size_t)img * p.blocks_per_image + p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_pw[comp] + bx;
+            int16_t *dst = p.coef + blk * 64;
+            if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
+            else quantize_store256<1>(p, v, dst);
+        }
+    }
+}
+
+template <int CT, int HS, int VS>
+cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
+    constexpr int BPP = Fmt<CT>::BPP;
+    const size_t smem = (size_t)4 * 256 * BPP * 8 * VS; // 4 warps per CTA, one private tile each
+    auto kernel = stage_a_warp_kernel<CT, HS, VS>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, n_sms = 0, ctas_per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    constexpr int MCUS = 32 / HS;
+    const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * p.mcu_rows * p.n_images;
+    unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm;
+    if (grid * 4 > n_tiles) grid = (n_tiles + 3) / 4;
+    kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename K>
+cudaError_t launch_persistent(K kernel, const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream);
+
 template <int CT, int HS, int VS, int NT, int MINB>
 cudaError_t launch_fast_v(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
+    return launch_persistent(stage_a_fast_kernel<CT, HS, VS, NT, MINB>, p, block, tile_bytes, stream);
+}
+
+template <typename K>
+cudaError_t launch_persistent(K kernel, const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
     const size_t smem = 2 * tile_bytes;
-    auto kernel = stage_a_fast_kernel<CT, HS, VS, NT, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, n_sms = 0, ctas_per_sm = 0;
@@ -502,15 +659,11 @@ cudaError_t launch_fast_v(const StageAParams &p, dim3 block, size_t tile_bytes, 
 
 template <int CT, int HS, int VS>
 cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
-    if (block.x <= 192) {
-        if constexpr (CT == JPGB_RGB && HS == 2 && VS == 2) { // experiment hook: occupancy variants
-            static const char *v = std::getenv("JPGB_STAGE_A_MINB");
-            if (v && v[0] == '3') return launch_fast_v<CT, HS, VS, 192, 3>(p, block, tile_bytes, stream);
-            if (v && v[0] == '4') return launch_fast_v<CT, HS, VS, 192, 4>(p, block, tile_bytes, stream);
-        }
-        // measured on B200 (C3): 2 CTAs x 128 registers beat 3 x 96 and 4 x 80 (spills, less ILP)
-        return launch_fast_v<CT, HS, VS, 192, 2>(p, block, tile_bytes, stream);
-    }
+    // Default: the warp-autonomous kernel (measured on B200, C3: 54 % of the HBM peak against 48 % for
+    // the CTA-tile kernel). JPGB_STAGE_A_VARIANT=cta selects the CTA-tile kernel for A/B runs.
+    static const char *v = std::getenv("JPGB_STAGE_A_VARIANT");
+    if (!(v && v[0] == 'c')) return launch_warp_variant<CT, HS, VS>(p, stream);
+    if (block.x <= 192) return launch_fast_v<CT, HS, VS, 192, 2>(p, block, tile_bytes, stream);
     return launch_fast_v<CT, HS, VS, 256, 2>(p, block, tile_bytes, stream);
 }
 
