@@ -71,7 +71,8 @@ struct jpgb_encoder {
     bool own_stream = false;
     std::string err;
     DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
-        scan_tmp, hist, piece_off, out2, pixels2;
+        scan_tmp, hist, piece_off, out2, pixels2, status;
+    double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
     PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out;
     int out_slot = 0; // which of out / out2 the next encode_device writes
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -235,7 +236,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     CK(enc->seglen.reserve(n_segs * 4), "alloc seglen");
     CK(enc->segpos.reserve((n_segs + 1) * 8), "alloc segpos");
     CK(enc->scan_tmp.reserve(scan_tmp_bytes(n_visits > n_segs ? n_visits : n_segs)), "alloc scan scratch");
-    CK(enc->h_small.reserve(64 + (size_t)(n + 1) * 8), "alloc readback");
 
     EntropyBuffers b{};
     b.plan = enc->plan.as<DevPlan>();
@@ -252,7 +252,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     b.hdr_stride = (uint32_t)hdr_stride;
     b.scan_tmp = enc->scan_tmp.p;
 
-    uint64_t ubytes = 0;
     {
         StageTimer t(enc, 2);
         CK(launch_symbol_sizes(b, hp, n, st), "symbol size launch");
@@ -260,63 +259,88 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
         CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches), "segment position scan");
         enc->launches += 2;
-        CK(cudaMemcpyAsync(enc->h_small.p, b.segpos + n_segs, 8, cudaMemcpyDeviceToHost, st), "read stream size");
     }
-    CK(cudaStreamSynchronize(st), "sizing sync");
-    ubytes = *enc->h_small.as<uint64_t>();
 
-    // ---- bit emission into the unstuffed stream ----
-    const uint64_t n_chunks = (ubytes + kStuffChunk - 1) / kStuffChunk;
-    CK(enc->ustream.reserve(((ubytes + 15) & ~(uint64_t)15) + 64), "alloc unstuffed stream");
-    CK(enc->raw_mask.reserve(((ubytes + 31) / 32 + 2) * 4), "alloc raw mask");
-    CK(enc->ffcount.reserve((n_chunks + 1) * 4), "alloc ff counts");
-    CK(enc->ffpos.reserve((n_chunks + 2) * 8), "alloc ff positions");
-    CK(enc->scan_tmp.reserve(scan_tmp_bytes(n_chunks)), "alloc scan scratch");
+    // ---- bit emission, stuffing, scatter: no host round trip. The unstuffed stream and the output are
+    // sized from what this context has seen before (first call: a fraction of the raw pixels); the kernels
+    // read the real sizes on the device and raise a flag instead of overrunning, in which case the tail of
+    // the pipeline is repeated once with exact sizes.
+    const uint64_t raw_bytes = (uint64_t)plan.p.width * plan.p.height * plan.bpp * n;
+    // learnt bytes per raw byte from earlier calls on this context, else a third of the raw size
+    uint64_t ucap = enc->ucap_ratio > 0 ? (uint64_t)(raw_bytes * enc->ucap_ratio) + (uint64_t)n * 4096 + 65536
+                                        : raw_bytes / 3 + (uint64_t)n * 4096 + 65536;
+    uint64_t ocap = ucap + ucap / 32 + 4096;
+    uint64_t ubytes = 0, total = 0;
     CK(enc->file_off.reserve((size_t)(n + 1) * 8), "alloc file offsets");
-    b.ustream = enc->ustream.as<uint8_t>();
-    b.raw_mask = enc->raw_mask.as<uint32_t>();
-    b.ffcount = enc->ffcount.as<uint32_t>();
-    b.ffpos = enc->ffpos.as<unsigned long long>();
+    CK(enc->status.reserve(32), "alloc status");
+    CK(enc->h_small.reserve(64 + (size_t)(n + 1) * 8), "alloc readback");
     b.file_off = enc->file_off.as<unsigned long long>();
-    b.scan_tmp = enc->scan_tmp.p;
-    {
-        StageTimer t(enc, 3);
-        CK(launch_zero_ustream(b, n_segs, st), "zero stream launch");
-        CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
-        CK(launch_emit_bits(b, hp, n, st), "emit launch");
-        enc->launches += 3;
-    }
-    // ---- 0xFF stuffing: count, scan, scatter ----
-    {
-        StageTimer t(enc, 4);
-        CK(launch_count_ff(b, ubytes, st), "count ff launch");
-        CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches), "ff scan");
-        enc->launches += 1;
-        CK(cudaMemcpyAsync(enc->h_small.p, b.ffpos + n_chunks, 8, cudaMemcpyDeviceToHost, st), "read ff total");
-    }
-    CK(cudaStreamSynchronize(st), "stuffing sync");
-    const uint64_t total = ubytes + *enc->h_small.as<uint64_t>();
-    DevBuf &outb = enc->out_slot ? enc->out2 : enc->out;
-    CK(outb.reserve(total + 64), "alloc output");
-    b.out = outb.as<uint8_t>();
-    {
-        StageTimer t(enc, 4);
-        CK(launch_stuff_scatter(b, ubytes, st), "scatter launch");
-        CK(launch_file_offsets(b, hp, n, ubytes, st), "file offsets launch");
-        enc->launches += 2;
-        CK(cudaMemcpyAsync(enc->h_small.p, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
-        if (piece_offsets) { // strip mode: where each scan's bytes start
-            const size_t np = plan.scans.size() + 1;
-            CK(enc->piece_off.reserve(np * 8), "alloc piece offsets");
-            CK(enc->h_pieces.reserve(np * 8), "alloc piece offsets (host)");
-            CK(launch_scan_offsets(b, hp, ubytes, enc->piece_off.as<unsigned long long>(), st), "scan offsets launch");
-            enc->launches += 1;
-            CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
+    b.status = enc->status.as<unsigned long long>();
+    b.n_segs_total = n_segs;
+    for (int attempt = 0;; ++attempt) {
+        ucap = (ucap + kStuffChunk - 1) / kStuffChunk * kStuffChunk;
+        const uint64_t n_chunks = ucap / kStuffChunk;
+        CK(enc->ustream.reserve(ucap + 64), "alloc unstuffed stream");
+        CK(enc->raw_mask.reserve((ucap / 32 + 2) * 4), "alloc raw mask");
+        CK(enc->ffcount.reserve((n_chunks + 1) * 4), "alloc ff counts");
+        CK(enc->ffpos.reserve((n_chunks + 2) * 8), "alloc ff positions");
+        CK(enc->scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(n_chunks, std::max(n_visits, n_segs)))), "alloc scan scratch");
+        DevBuf &outb = enc->out_slot ? enc->out2 : enc->out;
+        CK(outb.reserve(ocap + 64), "alloc output");
+        b.ustream = enc->ustream.as<uint8_t>();
+        b.raw_mask = enc->raw_mask.as<uint32_t>();
+        b.ffcount = enc->ffcount.as<uint32_t>();
+        b.ffpos = enc->ffpos.as<unsigned long long>();
+        b.scan_tmp = enc->scan_tmp.p;
+        b.out = outb.as<uint8_t>();
+        b.ustream_cap = ucap;
+        b.out_cap = ocap;
+        CK(cudaMemsetAsync(b.status, 0, 32, st), "clear status");
+        {
+            StageTimer t(enc, 3);
+            CK(launch_zero_ustream(b, n_segs, st), "zero stream launch");
+            CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
+            CK(launch_emit_bits(b, hp, n, st), "emit launch");
+            enc->launches += 3;
+        }
+        {
+            StageTimer t(enc, 4);
+            CK(launch_count_ff(b, st), "count ff launch");
+            CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches), "ff scan");
+            CK(launch_stuff_scatter(b, st), "scatter launch");
+            CK(launch_file_offsets(b, hp, n, st), "file offsets launch");
+            enc->launches += 3;
+            if (piece_offsets) { // strip mode: where each scan's bytes start
+                const size_t np = plan.scans.size() + 1;
+                CK(enc->piece_off.reserve(np * 8), "alloc piece offsets");
+                CK(enc->h_pieces.reserve(np * 8), "alloc piece offsets (host)");
+                CK(launch_scan_offsets(b, hp, enc->piece_off.as<unsigned long long>(), st), "scan offsets launch");
+                enc->launches += 1;
+                CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
+            }
+            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 32, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
+            CK(cudaMemcpyAsync(enc->h_small.p, b.status, 32, cudaMemcpyDeviceToHost, st), "read status");
+        }
+        CK(cudaStreamSynchronize(st), "final sync");
+        const uint64_t *status = enc->h_small.as<uint64_t>();
+        ubytes = status[0];
+        if (status[2] == 0) {
+            total = ubytes + status[1];
+            break;
+        }
+        if (attempt >= 2) return fail(enc, JPGB_ERR_CUDA, "internal: stream capacity retry did not converge");
+        // overflow: the sizing results are still on the device; redo the tail with room to spare
+        if (status[2] & 1) {
+            ucap = ubytes + ubytes / 16 + 65536;
+            ocap = ucap + ucap / 8 + 4096; // the 0xFF count is not known yet: generous
+        } else {
+            ocap = ubytes + status[1] + 4096;
         }
     }
+    enc->ucap_ratio = std::max(enc->ucap_ratio * 0.98, 1.15 * (double)ubytes / (double)std::max<uint64_t>(raw_bytes, 1));
     CK(cudaStreamSynchronize(st), "final sync");
     if (piece_offsets) piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
-    offsets.assign(enc->h_small.as<uint64_t>(), enc->h_small.as<uint64_t>() + n + 1);
+    offsets.assign(enc->h_small.as<uint64_t>() + 4, enc->h_small.as<uint64_t>() + 4 + n + 1);
     enc->out_total = total;
     if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
     return JPGB_OK;
@@ -484,7 +508,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
-                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2};
+                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
     e->h_hist.release();

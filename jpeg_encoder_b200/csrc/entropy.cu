@@ -260,8 +260,18 @@ __global__ void __launch_bounds__(256) segment_len_kernel(const EntropyBuffers b
     b.seglen[g] = lead_len(b, P, img, k, i) + (unsigned)((bits + 7) >> 3) + tail;
 }
 
+// Unstuffed stream size as computed on the device; kernels that write the stream bail out (and the
+// first one raises the overflow flag) when it exceeds the capacity the host provided.
+__device__ __forceinline__ unsigned long long stream_bytes(const EntropyBuffers &b) { return b.segpos[b.n_segs_total]; }
+__device__ __forceinline__ bool stream_fits(const EntropyBuffers &b) { return stream_bytes(b) <= b.ustream_cap; }
+
 __global__ void __launch_bounds__(256) zero_ustream_kernel(const EntropyBuffers b, unsigned long long n_segs_total) {
     const unsigned long long bytes = b.segpos[n_segs_total];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.status[0] = bytes;
+        if (bytes > b.ustream_cap) atomicOr(b.status + 2, 1ull);
+    }
+    if (bytes > b.ustream_cap) return;
     const unsigned long long n16 = (bytes + 15) >> 4, nm = ((bytes + 31) >> 5);
     uint4 *u = reinterpret_cast<uint4 *>(b.ustream);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
     // one warp per segment; lanes stride over the lead bytes (headers can be long: ICC, EXIF)
     const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (g >= n_segs) return;
+    if (g >= n_segs || !stream_fits(b)) return;
     const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.segs_per_image;
     const unsigned s = (unsigned)(g - img * P.segs_per_image);
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
 // writes the pad bits of finalize_bit_buffer (writer.rs:138-145: ones up to the byte boundary).
 __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_visits) return;
+    if (g >= n_visits || !stream_fits(b)) return;
     const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
     unsigned nb = b.nbits[g];
@@ -389,8 +399,9 @@ __device__ __forceinline__ unsigned ff_bits16(const uint4 d, unsigned raw16, uns
     return m;
 }
 
-__global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b, unsigned long long bytes) {
+__global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b) {
     __shared__ unsigned warp_sums[8];
+    const unsigned long long bytes = stream_fits(b) ? stream_bytes(b) : 0ull;
     const unsigned long long base = (unsigned long long)blockIdx.x * kStuffChunk + (unsigned long long)threadIdx.x * 16;
     unsigned cnt = 0;
     if (base < bytes) {
@@ -409,7 +420,18 @@ __global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b, u
     }
 }
 
-__global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers b, unsigned long long bytes) {
+__global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers b, unsigned long long n_chunks_cap) {
+    if (!stream_fits(b)) return;
+    const unsigned long long bytes = stream_bytes(b);
+    {
+        const unsigned long long ff_total = b.ffpos[n_chunks_cap];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            b.status[1] = ff_total;
+            if (bytes + ff_total > b.out_cap) atomicOr(b.status + 2, 2ull);
+        }
+        if (bytes + ff_total > b.out_cap) return;
+    }
+    if ((unsigned long long)blockIdx.x * kStuffChunk >= bytes) return;
     // The chunk's output is first laid out in shared memory at the same offset modulo 16 as its place
     // in `out`, then copied with aligned 128-bit stores (single bytes only at the two ends).
     __shared__ unsigned warp_excl[9];
@@ -468,7 +490,9 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
 
 // byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
 // bytes that precede it
-__global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers b, unsigned n_images, unsigned long long bytes) {
+__global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers b, unsigned n_images) {
+    if (!stream_fits(b)) return;
+    const unsigned long long bytes = stream_bytes(b);
     // one warp per file boundary; lanes stride over the (< kStuffChunk) bytes between the chunk start and it
     const unsigned img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -484,7 +508,9 @@ __global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers 
 }
 
 // final byte offset of the first segment of every scan of image 0 (+ the end): the pieces of a strip
-__global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers b, unsigned long long bytes, unsigned long long *offs) {
+__global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers b, unsigned long long *offs) {
+    if (!stream_fits(b)) return;
+    const unsigned long long bytes = stream_bytes(b);
     const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const DevPlan &P = *b.plan;
@@ -611,20 +637,21 @@ cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hp, uint32_
     place_bits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
     return cudaGetLastError();
 }
-cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {
-    count_ff_kernel<<<grid_for(bytes, kStuffChunk), 256, 0, s>>>(b, bytes);
+cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t s) {
+    count_ff_kernel<<<grid_for(b.ustream_cap, kStuffChunk), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
-cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t bytes, cudaStream_t s) {
-    stuff_scatter_kernel<<<grid_for(bytes, kStuffChunk), 256, 0, s>>>(b, bytes);
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t s) {
+    const unsigned long long n_chunks_cap = (b.ustream_cap + kStuffChunk - 1) / kStuffChunk;
+    stuff_scatter_kernel<<<grid_for(b.ustream_cap, kStuffChunk), 256, 0, s>>>(b, n_chunks_cap);
     return cudaGetLastError();
 }
-cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hp, uint64_t bytes, unsigned long long *offs, cudaStream_t s) {
-    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, bytes, offs);
+cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hp, unsigned long long *offs, cudaStream_t s) {
+    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, offs);
     return cudaGetLastError();
 }
-cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, uint64_t bytes, cudaStream_t s) {
-    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, n, bytes);
+cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, cudaStream_t s) {
+    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, n);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,10 @@ struct EntropyBuffers {
     uint8_t *out;                  // final files back to back
     unsigned long long *file_off;  // n + 1 offsets into `out`
     void *scan_tmp;                // scratch for the scans
+    // capacities (bytes) of ustream / out and the status block the kernels report into: the host sizes the
+    // buffers from the previous call and checks `status` once at the end instead of syncing mid-pipeline
+    unsigned long long ustream_cap, out_cap, n_segs_total;
+    unsigned long long *status;    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out)
     size_t scan_tmp_bytes;
 };
 
@@ -51,12 +55,11 @@ cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hplan
 cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t stream);
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
-cudaError_t launch_count_ff(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
-cudaError_t launch_stuff_scatter(const EntropyBuffers &b, uint64_t ustream_bytes, cudaStream_t stream);
-cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint64_t ustream_bytes, unsigned long long *offs,
+cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t stream);   // grids sized by b.ustream_cap
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t stream);
+cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, unsigned long long *offs,
                                 cudaStream_t stream);
-cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, uint64_t ustream_bytes,
-                                cudaStream_t stream);
+cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 
 // scan.cu -- device-wide exclusive prefix sum of u32 into u64; out has n + 1 entries (out[n] = total)
 size_t scan_tmp_bytes(uint64_t n);
