@@ -52,17 +52,6 @@ __device__ __forceinline__ int sample(const uint8_t *px, int comp) {
     return formula_cr(r, g, b);
 }
 
-__device__ __forceinline__ int fma_add(int a, int b) { // a + b as IMAD
-    int r;
-    asm("mad.lo.s32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ int fma_sub(int a, int b) { // a - b as IMAD
-    int r;
-    asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(r) : "r"(b), "r"(a));
-    return r;
-}
-
 // 1-D 8-point LL&M forward DCT (fdct.rs:116-171 for PASS 1, :178-237 for PASS 2).
 // PASS 1 takes *unshifted* samples 0..255: the -128 level shift (encoder.rs:1237) only moves the
 // DC term of the row by -128*8 << PASS1_BITS, every other output is a function of differences.
@@ -70,12 +59,10 @@ template <int PASS>
 __device__ __forceinline__ void dct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7) {
     constexpr int N = PASS == 1 ? 11 : 15; // CONST_BITS -/+ PASS1_BITS
     constexpr int RND = 1 << (N - 1);
-    // first butterflies on the FMA pipe (IMAD x*1+y): the ALU pipe carries the shifts, selects and
-    // remaining adds and is the busier of the two integer pipes (64 lanes/clk/SM each on B200)
-    const int tmp0 = fma_add(d7, d0), tmp7 = fma_sub(d0, d7);
-    const int tmp1 = fma_add(d6, d1), tmp6 = fma_sub(d1, d6);
-    const int tmp2 = fma_add(d5, d2), tmp5 = fma_sub(d2, d5);
-    const int tmp3 = fma_add(d4, d3), tmp4 = fma_sub(d3, d4);
+    const int tmp0 = d0 + d7, tmp7 = d0 - d7;
+    const int tmp1 = d1 + d6, tmp6 = d1 - d6;
+    const int tmp2 = d2 + d5, tmp5 = d2 - d5;
+    const int tmp3 = d3 + d4, tmp4 = d3 - d4;
     const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3;
     const int tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     if (PASS == 1) {
@@ -88,16 +75,17 @@ __device__ __forceinline__ void dct8(int &d0, int &d1, int &d2, int &d3, int &d4
     const int z1e = (tmp12 + tmp13) * 4433 + RND;      // FIX_0_541196100
     d2 = (z1e + tmp13 * 6270) >> N;                    // FIX_0_765366865
     d6 = (z1e - tmp12 * 15137) >> N;                   // FIX_1_847759065
-    const int z1 = tmp4 + tmp7, z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
-    const int z5 = (z3 + z4) * 9633 + RND;             // FIX_1_175875602
-    const int z3m = z5 - z3 * 16069;                   // FIX_1_961570560
-    const int z4m = z5 - z4 * 3196;                    // FIX_0_390180644
-    const int z1m = z1 * -7373;                        // FIX_0_899976223
-    const int z2m = z2 * -20995;                       // FIX_2_562915447
-    d7 = (tmp4 * 2446 + z1m + z3m) >> N;               // FIX_0_298631336
-    d5 = (tmp5 * 16819 + z2m + z4m) >> N;              // FIX_2_053119869
-    d3 = (tmp6 * 25172 + z2m + z3m) >> N;              // FIX_3_072711026
-    d1 = (tmp7 * 12299 + z1m + z4m) >> N;              // FIX_1_501321110
+    // Odd part with the constants combined per input (the integer sums are identical to fdct.rs:149-170
+    // term by term -- multiplication distributes exactly in two's complement):
+    //   z3' = z3*(c3 - c3c5) + z4*c3,  z4' = z3*c3 + z4*(c3 - c5c3)            [FIX_1_175875602 etc.]
+    //   out7 = tmp4*(0.298631336 - 0.899976223) - tmp7*0.899976223 + z3'   and so on.
+    const int z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
+    const int z3m = z3 * (9633 - 16069) + (z4 * 9633 + RND);
+    const int z4m = z3 * 9633 + (z4 * (9633 - 3196) + RND);
+    d7 = (tmp4 * (2446 - 7373) + (tmp7 * -7373 + z3m)) >> N;
+    d5 = (tmp5 * (16819 - 20995) + (tmp6 * -20995 + z4m)) >> N;
+    d3 = (tmp6 * (25172 - 20995) + (tmp5 * -20995 + z3m)) >> N;
+    d1 = (tmp7 * (12299 - 7373) + (tmp4 * -7373 + z4m)) >> N;
 }
 
 struct ZZ {
