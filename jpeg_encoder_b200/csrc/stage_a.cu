@@ -245,7 +245,8 @@ __device__ __forceinline__ int dot3(const uint32_t (&w)[NW]) {
     return acc;
 }
 
-enum Role { ROLE_Y = 0, ROLE_CB = 1, ROLE_CR = 2, ROLE_K = 3, ROLE_RAW = 4 };
+enum Role { ROLE_Y = 0, ROLE_CB = 1, ROLE_CR = 2, ROLE_K = 3, ROLE_RAW = 4, ROLE_CBCR = 5 };
+struct ChromaConsts;
 
 template <int CT>
 struct Fmt {
@@ -282,10 +283,58 @@ __device__ __forceinline__ void sample_row(const uint32_t (&w)[NW], int *s, std:
     ((s[Is] = sample_at<CT, ROLE, SX, Is, NW>(w)), ...);
 }
 
+// ---- Cb and Cr in one instruction stream (horizontally decimated chroma) -------------------------
+// In the warp-autonomous kernel lanes 0..15 produce Cb blocks and lanes 16..31 Cr blocks of the same
+// pixels. Both are  MID + M0*b[O] + M1*b[O+1] + M2*b[O+2]  with different coefficients, so the
+// coefficients travel in per-lane registers and every lane runs the same four IDP.2A: two in signed
+// 16-bit mode for the negative coefficients, two in unsigned mode for the +32768 one (which fits
+// neither s16 nor, together with a negative neighbour, u16). Pixels sit at even byte offsets here
+// (O = 2*BPP*i), so pair 0 holds (M0, M1) and pair 1 holds (M2, -).
+struct ChromaConsts {
+    uint32_t sA, sB, uA, uB; // signed pair 0 / pair 1, unsigned pair 0 / pair 1
+};
+template <int CT>
+__device__ __forceinline__ ChromaConsts chroma_consts(bool cr) {
+    auto pk = [](int a, int b) { return ((uint32_t)a & 0xFFFFu) | (((uint32_t)b & 0xFFFFu) << 16); };
+    ChromaConsts c;
+    if (!Fmt<CT>::BGR) { // memory order R, G, B
+        if (!cr) { c.sA = pk(-11059, -21709); c.sB = 0; c.uA = 0; c.uB = pk(32768, 0); }
+        else { c.sA = pk(0, -27439); c.sB = pk(-5329, 0); c.uA = pk(32768, 0); c.uB = 0; }
+    } else {             // memory order B, G, R
+        if (!cr) { c.sA = pk(0, -21709); c.sB = pk(-11059, 0); c.uA = pk(32768, 0); c.uB = 0; }
+        else { c.sA = pk(-5329, -27439); c.sB = 0; c.uA = 0; c.uB = pk(32768, 0); }
+    }
+    return c;
+}
+template <bool HI, bool SIGNED>
+__device__ __forceinline__ int idp2r(int acc, uint32_t coef, uint32_t w) {
+    int r;
+    if constexpr (HI && SIGNED) asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(w), "r"(acc));
+    else if constexpr (HI) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(w), "r"(acc));
+    else if constexpr (SIGNED) asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(w), "r"(acc));
+    else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(w), "r"(acc));
+    return r;
+}
+template <int O, int NW>
+__device__ __forceinline__ int chroma_at(const uint32_t (&w)[NW], const ChromaConsts &c) {
+    static_assert((O & 1) == 0, "decimated chroma pixels start at even byte offsets");
+    constexpr int P0 = O >> 1, P1 = P0 + 1;
+    int acc = (128 << 16) + 0x7FFF;
+    acc = idp2r<(P0 & 1) != 0, true>(acc, c.sA, w[P0 >> 1]);
+    acc = idp2r<(P1 & 1) != 0, true>(acc, c.sB, w[P1 >> 1]);
+    acc = idp2r<(P0 & 1) != 0, false>(acc, c.uA, w[P0 >> 1]);
+    acc = idp2r<(P1 & 1) != 0, false>(acc, c.uB, w[P1 >> 1]);
+    return acc >> 16;
+}
+template <int CT, int SX, int NW, int... Is>
+__device__ __forceinline__ void chroma_row(const uint32_t (&w)[NW], int *s, const ChromaConsts &c, std::integer_sequence<int, Is...>) {
+    ((s[Is] = chroma_at<Is * SX * Fmt<CT>::BPP, NW>(w, c)), ...);
+}
+
 // 8 samples (unshifted, 0..255) of one block row. `row` points at the first pixel of the row in the
 // shared tile; the pixels used are 0, SX, 2*SX, ... (point decimation, encoder.rs:1222-1242).
 template <int CT, int ROLE, int SX>
-__device__ __forceinline__ void load_row(const uint8_t *row, int *s) {
+__device__ __forceinline__ void load_row(const uint8_t *row, int *s, const ChromaConsts *cc = nullptr) {
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr int NW = (((7 * SX + 1) * BPP) + 3) / 4; // words spanned
     uint32_t w[NW];
@@ -326,13 +375,14 @@ __device__ __forceinline__ void load_row(const uint8_t *row, int *s) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[2 * i] = r[2 * i];
     }
-    sample_row<CT, ROLE, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
+    if constexpr (ROLE == ROLE_CBCR) chroma_row<CT, SX, NW>(w, s, *cc, std::make_integer_sequence<int, 8>{});
+    else sample_row<CT, ROLE, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
 }
 
 template <int CT, int ROLE, int SX, int SY>
-__device__ __forceinline__ void load_block(const uint8_t *base, int pitch, int (&v)[64]) {
+__device__ __forceinline__ void load_block(const uint8_t *base, int pitch, int (&v)[64], const ChromaConsts *cc = nullptr) {
 #pragma unroll
-    for (int y = 0; y < 8; ++y) load_row<CT, ROLE, SX>(base + y * SY * pitch, &v[y * 8]);
+    for (int y = 0; y < 8; ++y) load_row<CT, ROLE, SX>(base + y * SY * pitch, &v[y * 8], cc);
 }
 
 __device__ __forceinline__ void store256(void *dst, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
@@ -512,6 +562,8 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     constexpr int N_TASKS = N_FULL + N_CHROMA;
 
     const int lane = threadIdx.x & 31;
+    ChromaConsts cc{};
+    if constexpr (N_CHROMA == 1) cc = chroma_consts<CT>(lane >= 16);
     const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
     uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
@@ -577,6 +629,10 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             int v[64];
             if constexpr (CT == JPGB_LUMA) {
                 load_block<CT, ROLE_RAW, 1, 1>(base, PITCH, v);
+            } else if constexpr (N_CHROMA == 1) {
+                if (task >= N_FULL) load_block<CT, ROLE_CBCR, HS, VS>(base, PITCH, v, &cc); // lanes 0..15 Cb, 16..31 Cr
+                else if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, PITCH, v);
+                else load_block<CT, ROLE_K, 1, 1>(base, PITCH, v);
             } else {
                 if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, PITCH, v);
                 else if (comp == 1) load_block<CT, ROLE_CB, SUB ? HS : 1, SUB ? VS : 1>(base, PITCH, v);
