@@ -539,6 +539,16 @@ __device__ __forceinline__ void stage_a_fast_body(const StageAParams &p) {
     cp_async_wait<0>();
 }
 
+// Byte-wise fill of one 16-byte chunk with the row's last pixel replicated (Q4). Cold path, kept out of line.
+template <int BPP>
+__device__ __noinline__ void stage_edge_chunk(uint8_t *dst, const uint8_t *row, int cb, int valid_px) {
+    for (int b = 0; b < 16; ++b) {
+        const int byte = cb + b;
+        const int px = byte / BPP, ch = byte - px * BPP;
+        dst[cb + b] = row[min(px, valid_px - 1) * BPP + ch];
+    }
+}
+
 // =================================================================================================
 // Warp-autonomous variant. Every warp owns a private shared-memory tile of 32 full-resolution blocks
 // (256 pixels) x one MCU row and walks warp tiles on its own: cp.async its pixel rows, wait with
@@ -583,22 +593,16 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             const int valid_bytes = valid_px * BPP;
             const int needed_bytes = min(256, p.mcu_cols * 8 * HS - px0) * BPP;
             __syncwarp(); // all lanes are done reading the previous tile
-#pragma unroll 4
+#pragma unroll 1
             for (int ry = 0; ry < ROWS; ++ry) {
                 const int sy = min(py0 + ry, p.height - 1);
                 const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
                 uint8_t *dst = tile + ry * PITCH;
                 const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+#pragma unroll 1
                 for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
-                    if (aligned && cb + 16 <= valid_bytes) {
-                        cp_async16(dst + cb, row + cb);
-                    } else {
-                        for (int b = 0; b < 16; ++b) {
-                            const int byte = cb + b;
-                            const int px = byte / BPP, ch = byte - px * BPP;
-                            dst[cb + b] = row[min(px, valid_px - 1) * BPP + ch];
-                        }
-                    }
+                    if (aligned && cb + 16 <= valid_bytes) cp_async16(dst + cb, row + cb);
+                    else stage_edge_chunk<BPP>(dst, row, cb, valid_px); // cold: right edge / unaligned rows
                 }
             }
             cp_async_commit();
