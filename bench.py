@@ -296,7 +296,7 @@ def run_product(args):
     a_bytes = stage_a_bytes(width, height, color, cfg) * batch
     a_ms = stage_ms.get("colour_dct_quant", 0.0) / args.steps
     achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "stage_a_kernel (colour+decimate+fDCT+quant)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "stage_a_warp_kernel (colour+decimate+fDCT+quant)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": a_bytes, "ms_per_launch": a_ms,
                 "share_of_step": a_ms / ms_per_step if ms_per_step else None}
@@ -304,8 +304,9 @@ def run_product(args):
     if os.path.exists(traffic_path):
         try:
             tr = json.load(open(traffic_path))
-            if tr.get("workload") == args.workload:
-                roofline["traffic"] = tr.get("dram_bytes_per_launch_scaled_to_batch", {}).get(str(batch))
+            if tr.get("workload") == args.workload:  # ncu --set full capture of the same kernel, per frame x frames per launch
+                roofline["traffic"] = tr["dram_bytes_per_frame"] * batch
+                roofline["traffic_source"] = tr.get("source")
         except (ValueError, OSError):
             pass
 
