@@ -39,25 +39,23 @@ def split_pieces(buf, offsets):
 def gather_strip_pieces(local_bytes, piece_offsets, rank, world, device, group=None):
     """local_bytes: uint8 tensor on `device` holding this rank's pieces back to back.
     Returns on rank 0 the assembled uint8 tensor of the whole file (scan-major), on other ranks None.
-    Communication: one all_gather of the (n_scans + 1) offsets, then one send per non-zero rank."""
+    Communication: one all_gather of the (n_scans + 1) offsets, then ONE gather of the byte buffers to
+    rank 0 (padded to the longest; NCCL runs it as a single grouped send/recv over NVLink)."""
     n = len(piece_offsets)
     mine = torch.tensor(piece_offsets, dtype=torch.int64, device=device)
-    table = [torch.empty(n, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(table, mine, group=group)
-    table = [t.cpu().tolist() for t in table]
+    table = torch.empty(world * n, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(table, mine, group=group)
+    table = table.cpu().view(world, n).tolist()
+    longest = max(t[-1] for t in table)
+    send = local_bytes
+    if send.numel() < longest:  # pad (the context's buffer is usually larger than the file already)
+        send = torch.empty(longest, dtype=torch.uint8, device=device)
+        send[:local_bytes.numel()].copy_(local_bytes)
+    send = send[:longest]
     if rank == 0:
-        bufs = [local_bytes]
-        reqs = []
-        for r in range(1, world):
-            b = torch.empty(table[r][-1], dtype=torch.uint8, device=device)
-            bufs.append(b)
-            reqs.append(dist.irecv(b, src=r, group=group))
-        for q in reqs:
-            q.wait()
-        parts = []
-        for k in range(n - 1):
-            for r in range(world):
-                parts.append(bufs[r][table[r][k]:table[r][k + 1]])
+        bufs = [torch.empty(longest, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.gather(send, bufs, dst=0, group=group)
+        parts = [bufs[r][table[r][k]:table[r][k + 1]] for k in range(n - 1) for r in range(world)]
         return torch.cat(parts)
-    dist.send(local_bytes[:piece_offsets[-1]].contiguous(), dst=0, group=group)
+    dist.gather(send, None, dst=0, group=group)
     return None

@@ -211,6 +211,14 @@ def test_noise_and_extremes():
     _same("rgb", 320, 200, dict(quality=100, sampling=(1, 1)), img=ff)
 
 
+def test_maximum_dimensions():
+    """u16 limits of the API (src/encoder.rs:440-446): 65535 wide and 65535 tall."""
+    for w, h in ((65535, 9), (9, 65535)):
+        _same("rgb", w, h, dict(quality=80, sampling=(2, 2)), seed=3)
+        _same("luma", w, h, dict(quality=80, progressive_scans=3, restart_interval=999), seed=4)
+        _same("cmyk", w, h, dict(quality=80, sampling=(4, 2), optimize_huffman=True), seed=5)
+
+
 def test_density_and_trailing_bytes():
     _same("rgb", 33, 21, dict(quality=90, density=(1, 300, 300)))
     _same("rgb", 33, 21, dict(quality=90, density=(2, 118, 59)))
