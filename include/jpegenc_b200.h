@@ -100,6 +100,13 @@ typedef int (*jpgb_write_all_fn)(void *user, const uint8_t *buf, size_t len);
 int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len,
                         jpgb_write_all_fn write_all, void *user);
 
+/* Encoder::encode_image<I: ImageBuffer> (src/encoder.rs:506-515, trait at src/image_buffer.rs:86-98):
+ * the caller has already produced the component samples (what `fill_buffers` appends row by row).
+ * `p->color_type` names the JPEG colour type: JPGB_LUMA (1 plane), JPGB_YCBCR (3), JPGB_CMYK or
+ * JPGB_YCCK (4). planes[c] holds width*height samples of component c, taken verbatim. */
+int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len,
+                       uint8_t **out, size_t *out_len);
+
 /* Batch of `n` images of identical geometry and settings (BASELINE config 3; no reference
  * equivalent -- the crate is called once per image). Host memory in and out.
  * pixels[i] points at image i. outs[i]/out_lens[i] receive library-owned buffers (jpgb_free). */

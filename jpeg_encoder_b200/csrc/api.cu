@@ -541,6 +541,42 @@ int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, 
 
 void jpgb_free(void *buf) { std::free(buf); }
 
+int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len, uint8_t **out,
+                       size_t *out_len) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!p || !planes || !out || !out_len) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    *out = nullptr;
+    *out_len = 0;
+    const uint8_t ct = p->color_type;
+    if (ct != JPGB_LUMA && ct != JPGB_YCBCR && ct != JPGB_CMYK && ct != JPGB_YCCK)
+        return fail(enc, JPGB_ERR_BAD_PARAMS, "planar input takes a JPEG colour type: Luma, Ycbcr, Cmyk or Ycck");
+    const size_t plane_bytes = (size_t)p->width * p->height;
+    if (plane_len < plane_bytes) return fail(enc, JPGB_ERR_BAD_IMAGE_DATA, "plane shorter than width*height");
+    Plan plan;
+    plan.planar = true;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return fail(enc, rc, rc == JPGB_ERR_ZERO_DIMENSIONS ? "Image dimensions must be non zero" : "invalid parameters");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    timing_begin(enc);
+    const size_t stride = (plane_bytes * plan.ncomp + 255) & ~(size_t)255;
+    CK(enc->pixels.reserve(stride), "alloc planes");
+    for (int c = 0; c < plan.ncomp; ++c) {
+        if (!planes[c]) return fail(enc, JPGB_ERR_BAD_PARAMS, "null plane");
+        CK(cudaMemcpyAsync(enc->pixels.as<uint8_t>() + plane_bytes * c, planes[c], plane_bytes, cudaMemcpyHostToDevice, enc->stream), "upload plane");
+    }
+    std::vector<uint64_t> off;
+    const int rc2 = encode_device(enc, plan, enc->pixels.as<uint8_t>(), stride, 1, off);
+    if (rc2 != JPGB_OK) return rc2;
+    const size_t sz = (size_t)off[1];
+    *out = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
+    if (!*out) return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
+    CK(cudaMemcpyAsync(*out, enc->out.p, sz, cudaMemcpyDeviceToHost, enc->stream), "download file");
+    CK(cudaStreamSynchronize(enc->stream), "download sync");
+    *out_len = sz;
+    timing_end(enc);
+    return JPGB_OK;
+}
+
 int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len, jpgb_write_all_fn write_all,
                         void *user) {
     if (!write_all) return JPGB_ERR_BAD_PARAMS;

@@ -29,6 +29,8 @@ struct StageAParams {
     int tasks_per_group;   // warp tasks per group = sum over components of H_c*V_c
     int tile_w_px, tile_h_px, tile_pitch; // pitch in bytes
     int n_images;
+    int planar;            // 1: pixels = ncomp full-resolution planes of width*height bytes (plane_stride apart)
+    unsigned long long plane_stride;
     int use_fast;          // 1: stage_a_fast_kernel (task_h then holds the 32-block sub-run index)
     // per warp task inside a group: component and block position inside the MCU
     int8_t task_comp[kMaxSlots], task_v[kMaxSlots], task_h[kMaxSlots];

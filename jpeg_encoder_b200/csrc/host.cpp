@@ -512,9 +512,12 @@ void Plan::fill_stage_a(StageAParams &a) const {
     const bool fast_ct = p.color_type == JPGB_LUMA || (p.color_type >= JPGB_RGB && p.color_type <= JPGB_BGRA) ||
                          p.color_type == JPGB_CMYK_AS_YCCK;
     const char *fg = std::getenv("JPGB_FORCE_GENERIC_STAGE_A"); // test hook
-    a.use_fast = fast_ct && hmax <= 2 && vmax <= 2 && !force_generic_stage_a && !(fg && fg[0] == '1');
+    a.use_fast = !planar && fast_ct && hmax <= 2 && vmax <= 2 && !force_generic_stage_a && !(fg && fg[0] == '1');
     // CTA tile: `groups` x 32 MCUs wide, one MCU row high; aim for ~24 KB of pixels in shared memory
-    const int group_bytes = 32 * 8 * hmax * 8 * vmax * bpp;
+    a.planar = planar ? 1 : 0;
+    a.plane_stride = (unsigned long long)p.width * p.height;
+    if (planar) a.bpp = 1;
+    const int group_bytes = 32 * 8 * hmax * 8 * vmax * (planar ? ncomp : bpp);
     int g = std::max(1, 24576 / group_bytes);
     g = std::min(g, 8);
     g = std::min<int>(g, (int)((mcu_cols + 31) / 32));
@@ -522,7 +525,7 @@ void Plan::fill_stage_a(StageAParams &a) const {
     a.tiles_per_row = (int)((mcu_cols + 32 * g - 1) / (32 * g));
     a.tile_w_px = 32 * g * 8 * hmax;
     a.tile_h_px = 8 * vmax;
-    a.tile_pitch = a.tile_w_px * bpp;
+    a.tile_pitch = a.tile_w_px * (planar ? 1 : bpp);
     for (int t = 0; t < 2; ++t)
         for (int i = 0; i < 64; ++i) {
             const int32_t c = q[t].corr[i] * q[t].recip[i];

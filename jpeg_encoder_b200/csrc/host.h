@@ -65,6 +65,7 @@ struct Plan {
     std::vector<uint8_t> prefix; // SOI, APP0, [APP14], user APPn  (src/encoder.rs:536-554)
 
     // strip mode (strip != nullptr): geometry of the strip, header of the whole image
+    bool planar = false; // ImageBuffer path: one plane per component, samples taken verbatim
     bool is_strip = false;
     jpgb_strip strip{};
     int build(const jpgb_params &params, const jpgb_strip *strip = nullptr); // returns JPGB_* code

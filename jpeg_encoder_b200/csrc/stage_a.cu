@@ -35,9 +35,11 @@ __device__ __forceinline__ int formula_cr(int r, int g, int b) {
 }
 
 // One sample of component `comp` from the pixel at `px` (shared memory), unshifted 0..255.
+constexpr int kPlanar = 9; // internal: one full-resolution plane per component (the ImageBuffer path)
+
 template <int CT>
 __device__ __forceinline__ int sample(const uint8_t *px, int comp) {
-    if (CT == JPGB_LUMA) return px[0];
+    if (CT == JPGB_LUMA || CT == kPlanar) return px[0];
     if (CT == JPGB_YCBCR || CT == JPGB_YCCK) return px[comp];
     if (CT == JPGB_CMYK) return 255 - px[comp];
     int r, g, b;
@@ -126,7 +128,8 @@ __device__ __forceinline__ void quantize_store(const StageAParams &p, const int 
 template <int CT>
 __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ StageAParams p) {
     extern __shared__ __align__(16) uint8_t tile[];
-    constexpr int BPP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR || CT == JPGB_YCBCR) ? 3 : 4);
+    constexpr int BPP = (CT == JPGB_LUMA || CT == kPlanar) ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR || CT == JPGB_YCBCR) ? 3 : 4);
+    constexpr bool PLANAR = CT == kPlanar;
 
     const int tile_x = blockIdx.x, mcu_y = blockIdx.y, img = blockIdx.z;
     const int mcu_x0 = tile_x * 32 * p.groups;
@@ -139,11 +142,14 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
     const int n_chunks = chunks_per_row * p.tile_h_px;
     const int valid_px = min(p.tile_w_px, p.width - px0);  // > 0 by construction
     const int valid_bytes = valid_px * BPP;
-    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-        const int ry = c / chunks_per_row, cb = (c - ry * chunks_per_row) * 16;
+    const int plane_tile = p.tile_pitch * p.tile_h_px; // planar: one such tile per component, back to back
+    const int n_planes = PLANAR ? p.ncomp : 1;
+    for (int c = threadIdx.x; c < n_chunks * n_planes; c += blockDim.x) {
+        const int plane = c / n_chunks, cc = c - plane * n_chunks;
+        const int ry = cc / chunks_per_row, cb = (cc - ry * chunks_per_row) * 16;
         const int sy = min(py0 + ry, p.height - 1);
-        const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
-        uint8_t *dst = tile + ry * p.tile_pitch + cb;
+        const uint8_t *row = src + (size_t)plane * p.plane_stride + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+        uint8_t *dst = tile + plane * plane_tile + ry * p.tile_pitch + cb;
         if (cb + 16 <= valid_bytes && ((reinterpret_cast<uintptr_t>(row + cb) & 15) == 0)) {
             *reinterpret_cast<uint4 *>(dst) = __ldg(reinterpret_cast<const uint4 *>(row + cb));
         } else {
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
         // get_block arguments, encoder.rs:762-769: start = mcu*8*max + offset*8, stride = max/factor
         const int sx = p.hmax / p.comp_h[comp], sy = p.vmax / p.comp_v[comp];
         const int x0 = mcu_local * 8 * p.hmax + bh * 8, y0 = bv * 8;
-        const uint8_t *base = tile + y0 * p.tile_pitch + x0 * BPP;
+        const uint8_t *base = tile + (PLANAR ? comp * plane_tile : 0) + y0 * p.tile_pitch + x0 * BPP;
         const int step_x = sx * BPP, step_y = sy * p.tile_pitch;
 
         int v[64];
@@ -728,11 +734,11 @@ cudaError_t launch_fast_ct(const StageAParams &p, dim3 block, size_t smem, cudaS
 cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStream_t stream) {
     StageAParams p = p_in;
     p.n_images = (int)n_images;
-    const size_t smem = (size_t)p.tile_pitch * p.tile_h_px;
+    const size_t smem = (size_t)p.tile_pitch * p.tile_h_px * (p.planar ? p.ncomp : 1);
     const int n_tasks = p.groups * p.tasks_per_group;
     const int warps = n_tasks < 8 ? n_tasks : 8;
     dim3 grid(p.tiles_per_row, p.mcu_rows, n_images), block(warps * 32);
-    if (p.use_fast) {
+    if (p.use_fast && !p.planar) {
         switch (p.color_type) {
         case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, block, smem, stream);
         case JPGB_RGB: return launch_fast_ct<JPGB_RGB>(p, block, smem, stream);
@@ -752,7 +758,7 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
         stage_a_kernel<CT><<<grid, block, smem, stream>>>(p);                                                    \
         break;                                                                                                   \
     }
-    switch (p.color_type) {
+    switch (p.planar ? kPlanar : p.color_type) {
         JPGB_LAUNCH_A(JPGB_LUMA)
         JPGB_LAUNCH_A(JPGB_RGB)
         JPGB_LAUNCH_A(JPGB_RGBA)
@@ -762,6 +768,7 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
         JPGB_LAUNCH_A(JPGB_CMYK)
         JPGB_LAUNCH_A(JPGB_CMYK_AS_YCCK)
         JPGB_LAUNCH_A(JPGB_YCCK)
+        JPGB_LAUNCH_A(kPlanar)
     default: return cudaErrorInvalidValue;
     }
 #undef JPGB_LAUNCH_A

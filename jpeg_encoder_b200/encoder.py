@@ -35,6 +35,20 @@ class ColorType(enum.IntEnum):
         return (1, 3, 4, 3, 4, 3, 4, 4, 4)[int(self)]
 
 
+class JpegColorType(enum.IntEnum):
+    """src/encoder.rs:21-65 (colour type of the encoded file; what an ImageBuffer reports)"""
+    Luma = 0
+    Ycbcr = 1
+    Cmyk = 2
+    Ycck = 3
+
+    def get_num_components(self):
+        return (1, 3, 4, 4)[int(self)]
+
+    def as_color_type(self):
+        return (ColorType.Luma, ColorType.Ycbcr, ColorType.Cmyk, ColorType.Ycck)[int(self)]
+
+
 class SamplingFactor(enum.IntEnum):
     """src/encoder.rs:120-153 ((h << 4) | v; R_* aliases carry bit 0x80)"""
     F_1_1 = 1 << 4 | 1
@@ -170,6 +184,7 @@ def load_library():
     l.jpgb_encode_to_sink.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, vp, vp]
     l.jpgb_encode_batch.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.c_uint32,
                                     C.POINTER(u8p), C.POINTER(C.c_size_t)]
+    l.jpgb_encode_planar.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.POINTER(u8p), C.POINTER(C.c_size_t)]
     l.jpgb_encode_batch_pinned.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.c_uint32,
                                            C.POINTER(vp), C.POINTER(C.c_uint64)]
     l.jpgb_encode_batch_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32,
@@ -414,6 +429,39 @@ class Encoder:
             if err:
                 raise EncodingError(6, str(err[0])) from err[0]
             self._raise(rc)
+
+    # -- encode_image<I: ImageBuffer>, :506-515 --
+    def encode_image(self, image):
+        """`image` mirrors the ImageBuffer trait (src/image_buffer.rs:86-98): get_jpeg_color_type() ->
+        JpegColorType, width(), height(), fill_buffers(y, buffers) appending one row of samples to each
+        of up to four bytearrays. The rows are gathered on the host, the planes encoded on the GPU."""
+        jct = JpegColorType(image.get_jpeg_color_type())
+        w, h = image.width(), image.height()
+        ncomp = jct.get_num_components()
+        buffers = [bytearray() for _ in range(4)]
+        for y in range(h):
+            image.fill_buffers(y, buffers)
+        planes = [np.frombuffer(bytes(buffers[c]), dtype=np.uint8) for c in range(ncomp)]
+        return self.encode_planes(planes, w, h, jct)
+
+    def encode_planes(self, planes, width, height, jpeg_color_type):
+        """Component planes (width*height samples each, taken verbatim) -> JFIF bytes."""
+        dev = self._dev()
+        jct = JpegColorType(jpeg_color_type)
+        views = [_host_view(pl) for pl in planes]
+        if len(views) != jct.get_num_components():
+            raise ValueError("expected %d planes" % jct.get_num_components())
+        p = self._params(width, height, ColorType(jct.as_color_type()))
+        ptrs = (C.c_void_p * 4)(*([v.ctypes.data if v.size else None for v in views] + [None] * (4 - len(views))))
+        out = C.POINTER(C.c_uint8)()
+        n = C.c_size_t()
+        rc = dev.lib.jpgb_encode_planar(dev.handle, C.byref(p), ptrs, min(v.size for v in views), C.byref(out), C.byref(n))
+        if rc != 0:
+            self._raise(rc)
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            dev.lib.jpgb_free(out)
 
     def encode_batch(self, images, width, height, color_type):
         """n images of identical geometry (host memory) -> list of bytes. No reference equivalent."""

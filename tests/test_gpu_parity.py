@@ -336,3 +336,50 @@ def test_pipelined_host_batch_many_chunks():
     outs = make_encoder(cfg2).encode_batch([frames[i % 4] for i in range(20)], w, h, je.ColorType.Rgb)
     want2 = [oracle_encode(f, w, h, "rgb", cfg2) for f in frames]
     assert [o == want2[i % 4] for i, o in enumerate(outs)] == [True] * 20
+
+
+# ---- Encoder::encode_image<I: ImageBuffer> (src/encoder.rs:506-515): planar samples, taken verbatim ----
+class _RgbImageBuffer:
+    """The doc example of the trait (src/image_buffer.rs:48-84): an RGB image converted row by row."""
+
+    def __init__(self, rgb):
+        self.rgb = rgb
+
+    def get_jpeg_color_type(self):
+        import jpeg_encoder_b200 as je
+        return je.JpegColorType.Ycbcr
+
+    def width(self):
+        return self.rgb.shape[1]
+
+    def height(self):
+        return self.rgb.shape[0]
+
+    def fill_buffers(self, y, buffers):
+        r, g, b = (self.rgb[y, :, i].astype(np.int32) for i in range(3))
+        buffers[0] += ((19595 * r + 38470 * g + 7471 * b + 0x7FFF) >> 16).astype(np.uint8).tobytes()
+        buffers[1] += ((-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 0x7FFF) >> 16).astype(np.uint8).tobytes()
+        buffers[2] += ((32768 * r - 27439 * g - 5329 * b + (128 << 16) + 0x7FFF) >> 16).astype(np.uint8).tobytes()
+
+
+def test_encode_image_trait_equals_encode_rgb():
+    img = _img("rgb", 203, 131, seed=8)
+    for cfg in (dict(quality=88, sampling=(2, 2)), dict(quality=70, sampling=(4, 1), optimize_huffman=True),
+                dict(quality=95, sampling=(1, 1), progressive_scans=4, restart_interval=10)):
+        got = make_encoder(cfg).encode_image(_RgbImageBuffer(img))
+        assert got == oracle_encode(img, 203, 131, "rgb", cfg)
+
+
+@pytest.mark.parametrize("kind", ["luma", "ycbcr", "cmyk", "ycck"])
+def test_encode_planes_all_jpeg_color_types(kind):
+    import jpeg_encoder_b200 as je
+    w, h = 150, 91
+    jct = {"luma": je.JpegColorType.Luma, "ycbcr": je.JpegColorType.Ycbcr, "cmyk": je.JpegColorType.Cmyk, "ycck": je.JpegColorType.Ycck}[kind]
+    n = jct.get_num_components()
+    planes = [images.photo_like(w, h, 1, seed=30 + c) for c in range(n)]
+    packed = planes[0] if n == 1 else np.stack(planes, -1)
+    for cfg in (dict(quality=80, sampling=(2, 2)), dict(quality=80, sampling=(2, 4), restart_interval=6), dict(quality=80, sampling=(1, 2), progressive_scans=3)):
+        got = make_encoder(cfg).encode_planes(planes, w, h, jct)
+        # the packed adaptors copy Luma/Ycbcr/Ycck samples verbatim and invert Cmyk (src/image_buffer.rs:115-121, 221-229, 247-256, 303-312)
+        ref_in = 255 - packed if kind == "cmyk" else packed
+        assert got == oracle_encode(ref_in, w, h, kind, cfg)
