@@ -599,16 +599,32 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             const int valid_bytes = valid_px * BPP;
             const int needed_bytes = min(256, p.mcu_cols * 8 * HS - px0) * BPP;
             __syncwarp(); // all lanes are done reading the previous tile
+            const bool interior = px0 + 256 <= p.width && py0 + ROWS <= p.height && (row_bytes & 15) == 0 &&
+                                  ((reinterpret_cast<uintptr_t>(src) + (size_t)px0 * BPP) & 15) == 0;
+            if (interior) {
+                // whole tile inside the image and 16-byte aligned: every lane copies its fixed chunks of each row
+                const uint8_t *g = src + (size_t)py0 * row_bytes + (size_t)px0 * BPP + lane * 16;
+                uint8_t *d = tile + lane * 16;
+#pragma unroll 4
+                for (int ry = 0; ry < ROWS; ++ry) {
+#pragma unroll
+                    for (int c = 0; c < (PITCH + 511) / 512; ++c)
+                        if (c * 512 + 512 <= PITCH || lane * 16 + c * 512 < PITCH) cp_async16(d + c * 512, g + c * 512);
+                    g += row_bytes;
+                    d += PITCH;
+                }
+            } else {
 #pragma unroll 1
-            for (int ry = 0; ry < ROWS; ++ry) {
-                const int sy = min(py0 + ry, p.height - 1);
-                const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
-                uint8_t *dst = tile + ry * PITCH;
-                const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+                for (int ry = 0; ry < ROWS; ++ry) {
+                    const int sy = min(py0 + ry, p.height - 1);
+                    const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
+                    uint8_t *dst = tile + ry * PITCH;
+                    const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 #pragma unroll 1
-                for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
-                    if (aligned && cb + 16 <= valid_bytes) cp_async16(dst + cb, row + cb);
-                    else stage_edge_chunk<BPP>(dst, row, cb, valid_px); // cold: right edge / unaligned rows
+                    for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
+                        if (aligned && cb + 16 <= valid_bytes) cp_async16(dst + cb, row + cb);
+                        else stage_edge_chunk<BPP>(dst, row, cb, valid_px); // cold: right edge / unaligned rows
+                    }
                 }
             }
             cp_async_commit();
