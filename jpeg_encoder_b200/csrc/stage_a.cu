@@ -555,6 +555,14 @@ __device__ __noinline__ void stage_edge_chunk(uint8_t *dst, const uint8_t *row, 
     }
 }
 
+// MCU rows per warp tile: formats whose one-MCU-row tile is small (grayscale: 2 KB, one task) take several
+// rows per tile so that the staging and bookkeeping are amortised over more blocks.
+template <int CT, int HS, int VS>
+__host__ __device__ constexpr int warp_tile_mcu_rows() {
+    constexpr int bytes = 256 * Fmt<CT>::BPP * 8 * VS;
+    return bytes <= 2048 ? 4 : (bytes <= 6144 ? 2 : 1);
+}
+
 // =================================================================================================
 // Warp-autonomous variant. Every warp owns a private shared-memory tile of 32 full-resolution blocks
 // (256 pixels) x one MCU row and walks warp tiles on its own: cp.async its pixel rows, wait with
@@ -568,14 +576,17 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;
     constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
-    constexpr int ROWS = 8 * VS;
+    constexpr int MR = warp_tile_mcu_rows<CT, HS, VS>(); // MCU rows per warp tile (small tiles take several)
+    constexpr int MROWS = 8 * VS;               // pixel rows of one MCU row
+    constexpr int ROWS = MROWS * MR;
     constexpr int PITCH = 256 * BPP;            // 32 full-resolution blocks wide
     constexpr int TILE_BYTES = PITCH * ROWS;
     constexpr int MCUS = 32 / HS;               // MCUs per warp tile
     // tasks of one warp tile: luma rows, [K rows], then chroma
     constexpr int N_FULL = (NCOMP == 4 ? 2 : 1) * VS;
     constexpr int N_CHROMA = NCOMP == 1 ? 0 : (SUB && HS == 2 ? 1 : 2); // Cb+Cr share a task when 16 blocks each
-    constexpr int N_TASKS = N_FULL + N_CHROMA;
+    constexpr int N_TASKS_ROW = N_FULL + N_CHROMA;
+    constexpr int N_TASKS = N_TASKS_ROW * MR;
 
     const int lane = threadIdx.x & 31;
     ChromaConsts cc{};
@@ -584,16 +595,17 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
     uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
     const unsigned tiles_per_row = ((unsigned)p.mcu_cols + MCUS - 1) / MCUS;
-    const unsigned n_tiles = tiles_per_row * p.mcu_rows * p.n_images;
+    const unsigned tile_rows = ((unsigned)p.mcu_rows + MR - 1) / MR;
+    const unsigned n_tiles = tiles_per_row * tile_rows * p.n_images;
     const size_t row_bytes = (size_t)p.width * BPP;
 
     for (unsigned t = warp_global; t < n_tiles; t += n_warps_total) {
         const unsigned tx = t % tiles_per_row, r = t / tiles_per_row;
-        const int mcu_y = (int)(r % (unsigned)p.mcu_rows), img = (int)(r / (unsigned)p.mcu_rows);
+        const int mcu_y0 = (int)(r % tile_rows) * MR, img = (int)(r / tile_rows);
         const int mcu_x0 = (int)tx * MCUS;
         // ---- stage this warp's rows (cp.async, L2 only); edges replicated (Q4) ----
         {
-            const int px0 = mcu_x0 * 8 * HS, py0 = mcu_y * ROWS;
+            const int px0 = mcu_x0 * 8 * HS, py0 = mcu_y0 * MROWS;
             const uint8_t *src = p.pixels + (size_t)img * p.image_stride;
             const int valid_px = min(256, p.width - px0);
             const int valid_bytes = valid_px * BPP;
@@ -633,7 +645,11 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
         }
         // ---- tasks ----
 #pragma unroll 1
-        for (int task = 0; task < N_TASKS; ++task) {
+        for (int task_all = 0; task_all < N_TASKS; ++task_all) {
+            const int mr = MR == 1 ? 0 : task_all / N_TASKS_ROW, task = MR == 1 ? task_all : task_all - mr * N_TASKS_ROW;
+            const int mcu_y = mcu_y0 + mr;
+            if (mcu_y >= p.mcu_rows) break;
+            const uint8_t *mtile = tile + mr * MROWS * PITCH; // this MCU row's pixel rows inside the tile
             int comp, bv = 0, bxl = lane; // component, block row inside the MCU row, block column inside the tile
             bool full = true;
             if (task < N_FULL) {
@@ -650,7 +666,7 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             const int H = full ? HS : 1, V = full ? VS : 1;
             const int bx = mcu_x0 * H + bxl;
             if (bx >= p.comp_pw[comp]) continue;
-            const uint8_t *base = full ? tile + (bv * 8) * PITCH + bxl * 8 * BPP : tile + bxl * 8 * HS * BPP;
+            const uint8_t *base = full ? mtile + (bv * 8) * PITCH + bxl * 8 * BPP : mtile + bxl * 8 * HS * BPP;
 
             int v[64];
             if constexpr (CT == JPGB_LUMA) {
@@ -683,7 +699,8 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
 template <int CT, int HS, int VS>
 cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     constexpr int BPP = Fmt<CT>::BPP;
-    const size_t smem = (size_t)4 * 256 * BPP * 8 * VS; // 4 warps per CTA, one private tile each
+    constexpr int MR = warp_tile_mcu_rows<CT, HS, VS>();
+    const size_t smem = (size_t)4 * 256 * BPP * 8 * VS * MR; // 4 warps per CTA, one private tile each
     auto kernel = stage_a_warp_kernel<CT, HS, VS>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -694,7 +711,7 @@ cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     constexpr int MCUS = 32 / HS;
-    const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * p.mcu_rows * p.n_images;
+    const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * ((p.mcu_rows + MR - 1) / MR) * p.n_images;
     unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm;
     if (grid * 4 > n_tiles) grid = (n_tiles + 3) / 4;
     kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
