@@ -58,6 +58,30 @@ __device__ __forceinline__ int find_scan_by_seg(const DevPlan &P, unsigned s) {
     return lo;
 }
 
+// g = img * visits_per_image + v. 64-bit division is ~100 instructions on the GPU; nearly every call has
+// both numbers below 2^32, where the 32-bit divide is a handful.
+__device__ __forceinline__ void split_visit(const DevPlan &P, unsigned long long g, unsigned long long &img, unsigned long long &v) {
+    if ((g >> 32) == 0 && (P.visits_per_image >> 32) == 0) {
+        const unsigned q = (unsigned)g / (unsigned)P.visits_per_image;
+        img = q;
+        v = (unsigned)g - q * (unsigned)P.visits_per_image;
+    } else {
+        img = g / P.visits_per_image;
+        v = g - img * P.visits_per_image;
+    }
+}
+// unit and slot of a visit inside its scan; a scan has < 2^32 visits (<= 2^26 blocks x 18 per unit)
+__device__ __forceinline__ void split_unit(const DevScan &S, unsigned long long v, unsigned &unit, unsigned &slot) {
+    const unsigned rel = (unsigned)(v - S.visit_base);
+    if (S.bpu == 1) {
+        unit = rel;
+        slot = 0;
+    } else {
+        unit = rel / S.bpu;
+        slot = rel - unit * S.bpu;
+    }
+}
+
 // Where does visit `v` (numbered within one image) live, and what precedes it?
 // Interleaved order: encoder.rs:747-791 (MCU raster; component, v, h inside the MCU).
 // Single-component order: encoder.rs:832 / 894 / 946 over encode_blocks' raster grid (:1030-1031).
@@ -66,10 +90,11 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
     VisitInfo r;
     const int k = find_scan_by_visit(P, v);
     const DevScan &S = P.scans[k];
-    const unsigned long long rel = v - S.visit_base;
-    const unsigned unit = (unsigned)(rel / S.bpu), slot = (unsigned)(rel - (unsigned long long)unit * S.bpu);
+    unsigned unit, slot;
+    split_unit(S, v, unit, slot);
     const unsigned R = (unsigned)P.restart;
-    const bool restart_here = unit == 0 || (R && unit % R == 0);
+    const unsigned seg_q = R ? unit / R : 0, seg_r = R ? unit - seg_q * R : unit; // unit = seg_q * R + seg_r
+    const bool restart_here = unit == 0 || (R && seg_r == 0);
     unsigned long long blk, pred = 0;
     bool has_pred = true;
     int comp;
@@ -106,10 +131,10 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
     r.se = S.se;
     r.tbl = P.comp_tbl[comp];
     r.scan = k;
-    r.seg_in_scan = R ? unit / R : 0;
+    r.seg_in_scan = seg_q;
     r.seg_local = S.seg_base + r.seg_in_scan;
     r.first_visit_of_seg = S.visit_base + (unsigned long long)r.seg_in_scan * R * S.bpu;
-    r.last_of_seg = slot == S.bpu - 1 && (unit == S.n_units - 1 || (R && (unit + 1) % R == 0));
+    r.last_of_seg = slot == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
     return r;
 }
 
@@ -223,7 +248,8 @@ __global__ void __launch_bounds__(256) encode_visits_kernel(const EntropyBuffers
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_visits) return;
     const DevPlan &P = *b.plan;
-    const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
+    unsigned long long img, v;
+    split_visit(P, g, img, v);
     const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
     BitSink sink(b.slots, n_visits, g);
     if (vi.ss == 0 && vi.se == 63) code_visit<true>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
@@ -326,16 +352,17 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_visits || !stream_fits(b)) return;
     const DevPlan &P = *b.plan;
-    const unsigned long long img = g / P.visits_per_image, v = g - img * P.visits_per_image;
+    unsigned long long img, v;
+    split_visit(P, g, img, v);
     unsigned nb = b.nbits[g];
     // segment bookkeeping only (no coefficient access)
     const int k = find_scan_by_visit(P, v);
     const DevScan &S = P.scans[k];
-    const unsigned long long rel = v - S.visit_base;
-    const unsigned unit = (unsigned)(rel / S.bpu), slot_in_unit = (unsigned)(rel - (unsigned long long)unit * S.bpu);
+    unsigned unit, slot_in_unit;
+    split_unit(S, v, unit, slot_in_unit);
     const unsigned R = (unsigned)P.restart;
     const unsigned seg_in_scan = R ? unit / R : 0;
-    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && (unit + 1) % R == 0));
+    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && unit - seg_in_scan * R == R - 1));
     if (nb == 0 && !last_of_seg) return;
     const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
     const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
@@ -488,6 +515,19 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
     }
 }
 
+// data 0xFF bytes in [chunk start, pos) of the unstuffed stream, counted by one warp with 128-bit loads
+__device__ __forceinline__ unsigned ff_before_in_chunk(const EntropyBuffers &b, unsigned long long pos, int lane) {
+    const unsigned long long start = pos / kStuffChunk * kStuffChunk;
+    unsigned ff = 0;
+    for (unsigned long long i = start + (unsigned long long)lane * 16; i < pos; i += 32 * 16) {
+        const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + i);
+        const unsigned raw = (b.raw_mask[i >> 5] >> (i & 31)) & 0xFFFFu;
+        const unsigned valid = pos - i < 16 ? (unsigned)(pos - i) : 16u;
+        ff += __popc(ff_bits16(d, raw, valid));
+    }
+    return __reduce_add_sync(0xffffffffu, ff);
+}
+
 // byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
 // bytes that precede it
 __global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers b, unsigned n_images) {
@@ -500,10 +540,7 @@ __global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers 
     const DevPlan &P = *b.plan;
     const unsigned long long pos = img == n_images ? bytes : b.segpos[(unsigned long long)img * P.segs_per_image];
     const unsigned long long chunk = pos / kStuffChunk;
-    unsigned ff = 0;
-    for (unsigned long long i = chunk * kStuffChunk + lane; i < pos; i += 32)
-        if (b.ustream[i] == 0xFF && !((b.raw_mask[i >> 5] >> (i & 31)) & 1u)) ++ff;
-    ff = __reduce_add_sync(0xffffffffu, ff);
+    const unsigned ff = ff_before_in_chunk(b, pos, lane);
     if (lane == 0) b.file_off[img] = pos + b.ffpos[chunk] + ff;
 }
 
@@ -517,10 +554,7 @@ __global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers 
     if (k > (unsigned)P.n_scans) return;
     const unsigned long long pos = k == (unsigned)P.n_scans ? bytes : b.segpos[P.scans[k].seg_base];
     const unsigned long long chunk = pos / kStuffChunk;
-    unsigned ff = 0;
-    for (unsigned long long i = chunk * kStuffChunk + lane; i < pos; i += 32)
-        if (b.ustream[i] == 0xFF && !((b.raw_mask[i >> 5] >> (i & 31)) & 1u)) ++ff;
-    ff = __reduce_add_sync(0xffffffffu, ff);
+    const unsigned ff = ff_before_in_chunk(b, pos, lane);
     if (lane == 0) offs[k] = pos + b.ffpos[chunk] + ff;
 }
 
