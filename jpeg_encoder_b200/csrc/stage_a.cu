@@ -15,7 +15,10 @@
 // shuffles, no shared-memory round trip, no divergence. Each lane then writes its 128-byte block.
 //
 // All arithmetic is 32-bit integer; tensor cores are not used (the DCT must be bit-exact).
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 
 #include "kernels.h"
@@ -127,7 +130,7 @@ __device__ __forceinline__ void quantize_store(const StageAParams &p, const int 
 
 template <int CT>
 __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ StageAParams p) {
-    extern __shared__ __align__(16) uint8_t tile[];
+    extern __shared__ __align__(128) uint8_t tile[];
     constexpr int BPP = (CT == JPGB_LUMA || CT == kPlanar) ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR || CT == JPGB_YCBCR) ? 3 : 4);
     constexpr bool PLANAR = CT == kPlanar;
 
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(NT, MINB) stage_a_fast_kernel(const __grid_con
 }
 template <int CT, int HS, int VS, int NT, int MINB>
 __device__ __forceinline__ void stage_a_fast_body(const StageAParams &p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;                         // are there subsampled (1x1) components?
     constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
@@ -555,6 +558,30 @@ __device__ __noinline__ void stage_edge_chunk(uint8_t *dst, const uint8_t *row, 
     }
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier, one barrier per warp --------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(phase) : "memory");
+}
+// one 3-D box (x in 4-byte elements, y in pixel rows, z = image) -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
 // MCU rows per warp tile: formats whose one-MCU-row tile is small (grayscale: 2 KB, one task) take several
 // rows per tile so that the staging and bookkeeping are amortised over more blocks.
 template <int CT, int HS, int VS>
@@ -571,8 +598,9 @@ __host__ __device__ constexpr int warp_tile_mcu_rows() {
 // role imbalance between warps; the other resident warps hide a warp's load latency.
 // =================================================================================================
 template <int CT, int HS, int VS>
-__global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_constant__ StageAParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_constant__ StageAParams p,
+                                                              const __grid_constant__ CUtensorMap tmap, const int use_tma) {
+    extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;
     constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
@@ -594,6 +622,16 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
     uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
+    // one mbarrier per warp behind the four tiles: TMA signals the bytes of this warp's tile on it
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 * TILE_BYTES) + (threadIdx.x >> 5);
+    unsigned phase = 0;
+    if (use_tma) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const unsigned tiles_per_row = ((unsigned)p.mcu_cols + MCUS - 1) / MCUS;
     const unsigned tile_rows = ((unsigned)p.mcu_rows + MR - 1) / MR;
     const unsigned n_tiles = tiles_per_row * tile_rows * p.n_images;
@@ -613,7 +651,17 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             __syncwarp(); // all lanes are done reading the previous tile
             const bool interior = px0 + 256 <= p.width && py0 + ROWS <= p.height && (row_bytes & 15) == 0 &&
                                   ((reinterpret_cast<uintptr_t>(src) + (size_t)px0 * BPP) & 15) == 0;
-            if (interior) {
+            if (interior && use_tma) {
+                // One TMA box per tile (UTMALDG): a single lane issues it, the tensor unit streams the
+                // 256-pixel x ROWS box into this warp's tile and signals the byte count on the warp's mbarrier.
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic-proxy accesses of the tile
+                    mbar_expect_tx(bar, TILE_BYTES);
+                    tma_load_3d(tile, &tmap, bar, px0 * BPP / 4, py0, img);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            } else if (interior) {
                 // whole tile inside the image and 16-byte aligned: every lane copies its fixed chunks of each row
                 const uint8_t *g = src + (size_t)py0 * row_bytes + (size_t)px0 * BPP + lane * 16;
                 uint8_t *d = tile + lane * 16;
@@ -696,11 +744,41 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// Tensor map of the packed pixels as a 3-D tensor of 4-byte elements: (row bytes / 4, rows, images), box =
+// one warp tile. Needs 16-byte aligned base, row pitch and image pitch; otherwise the kernel stages with cp.async.
+inline bool make_pixel_tensor_map(CUtensorMap &map, const StageAParams &p, int bpp, int pitch_bytes, int rows) {
+    const unsigned long long row_bytes = (unsigned long long)p.width * bpp;
+    if (std::getenv("JPGB_NO_TMA")) return false;
+    if ((reinterpret_cast<uintptr_t>(p.pixels) & 15) || (row_bytes & 15) || (p.image_stride & 15) || p.width < 256 || p.height < rows) return false;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)p.height, (cuuint64_t)p.n_images};
+    const cuuint64_t strides[2] = {row_bytes, p.image_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(pitch_bytes / 4), (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(p.pixels), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CT, int HS, int VS>
 cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr int MR = warp_tile_mcu_rows<CT, HS, VS>();
-    const size_t smem = (size_t)4 * 256 * BPP * 8 * VS * MR; // 4 warps per CTA, one private tile each
+    constexpr int TILE = 256 * BPP * 8 * VS * MR;
+    const size_t smem = (size_t)4 * TILE + 4 * sizeof(uint64_t); // 4 warps per CTA: one private tile and one mbarrier each
     auto kernel = stage_a_warp_kernel<CT, HS, VS>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -714,7 +792,10 @@ cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * ((p.mcu_rows + MR - 1) / MR) * p.n_images;
     unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm;
     if (grid * 4 > n_tiles) grid = (n_tiles + 3) / 4;
-    kernel<<<(unsigned)grid, 128, smem, stream>>>(p);
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    const int use_tma = make_pixel_tensor_map(tmap, p, BPP, 256 * BPP, 8 * VS * MR) ? 1 : 0;
+    kernel<<<(unsigned)grid, 128, smem, stream>>>(p, tmap, use_tma);
     return cudaGetLastError();
 }
 
