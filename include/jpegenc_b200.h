@@ -192,6 +192,17 @@ int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]);
 /* number of kernel launches issued by the last jpgb_encode* / jpgb_stage_a_device call */
 uint32_t jpgb_encoder_last_launch_count(const jpgb_encoder *enc);
 
+/* ---- host-side planner, callable without a GPU (used by the CPU test-suite) ---------------------- */
+
+/* The file header the encoder writes for `p` with the default (Annex K.3) Huffman tables: SOI, APP0,
+ * [APP14], user APPn, SOF, DQT x2, DHT x2|4, [DRI], first SOS (src/encoder.rs:536-554, 633-667, 705).
+ * Writes up to `cap` bytes to `buf`, the full length to *len. */
+int jpgb_build_header(const jpgb_params *p, uint8_t *buf, size_t cap, size_t *len);
+
+/* HuffmanTable::new_optimized (Annex K.2, src/huffman.rs:99-221) as the host planner runs it on the
+ * device histogram: code-length counts, values in code order, number of values. */
+int jpgb_optimized_huffman_table(const uint32_t freq[257], uint8_t length[16], uint8_t values[256], uint32_t *n_values);
+
 const char *jpgb_version(void);
 
 #ifdef __cplusplus

@@ -738,6 +738,31 @@ int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]) {
 }
 uint32_t jpgb_encoder_last_launch_count(const jpgb_encoder *enc) { return enc ? enc->launches : 0; }
 
+int jpgb_build_header(const jpgb_params *p, uint8_t *buf, size_t cap, size_t *len) {
+    if (!p || !len) return JPGB_ERR_BAD_PARAMS;
+    Plan plan;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return rc;
+    HuffTable huff[2][2];
+    default_huffman_tables(huff);
+    std::vector<uint8_t> h = plan.prefix;
+    plan.frame_header(huff, h);
+    h.insert(h.end(), plan.scans[0].sos.begin(), plan.scans[0].sos.end());
+    *len = h.size();
+    if (buf) std::memcpy(buf, h.data(), std::min(cap, h.size()));
+    return JPGB_OK;
+}
+
+int jpgb_optimized_huffman_table(const uint32_t freq[257], uint8_t length[16], uint8_t values[256], uint32_t *n_values) {
+    if (!freq || !length || !values || !n_values) return JPGB_ERR_BAD_PARAMS;
+    HuffTable t;
+    if (!t.set_optimized(freq)) return JPGB_ERR_HUFFMAN;
+    std::memcpy(length, t.length, 16);
+    std::memcpy(values, t.values.data(), t.values.size());
+    *n_values = (uint32_t)t.values.size();
+    return JPGB_OK;
+}
+
 const char *jpgb_version(void) { return "jpeg-encoder_b200 0.1 (sm_100a; parity target: jpeg-encoder 0.7.0)"; }
 
 } // extern "C"

@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
 
 // =================================================================================================
 // Fast path (the BASELINE configurations): Luma, the RGB family and CmykAsYcck at luma sampling
-// 1x1 / 2x1 / 1x2 / 2x2. Same tile, same one-block-per-lane decomposition, but
-//   * a warp task is 32 *consecutive blocks of one component block row*, so the 32 lanes read
+// 1x1 / 2x1 / 1x2 / 2x2. Same one-block-per-lane decomposition as the generic kernel, but
+//   * a task is 32 *consecutive blocks of one component block row*, so the 32 lanes read
 //     adjacent 8-pixel spans (bank-conflict-free 64/128-bit shared loads) and write one contiguous
 //     4 KB run of coefficients with 256-bit stores;
 //   * colour conversion runs on packed pixel words with IDP.2A (dp2a: two 16-bit coefficients x
@@ -425,128 +425,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct TileCoord {
-    int img, mcu_y, mcu_x0;
-};
-__device__ __forceinline__ TileCoord tile_coord(const StageAParams &p, unsigned t) {
-    TileCoord c;
-    const unsigned tx = t % (unsigned)p.tiles_per_row, r = t / (unsigned)p.tiles_per_row;
-    c.mcu_y = (int)(r % (unsigned)p.mcu_rows);
-    c.img = (int)(r / (unsigned)p.mcu_rows);
-    c.mcu_x0 = (int)tx * 32 * p.groups;
-    return c;
-}
-
-// Stage one tile (8*VS pixel rows x tile_pitch bytes) into shared memory. Whole 16-byte chunks inside
-// the image go through cp.async (LDGSTS, L2 only: the pixels are read exactly once); chunks that hold
-// the right edge are filled byte-wise with the row's last pixel replicated (Q4: encoder.rs:738-744);
-// chunks past the last MCU of the row are never read and are skipped. Rows past the bottom re-read
-// the last image row (:734). Warps take rows, lanes take chunks: no divisions.
-template <int BPP, int VS>
-__device__ __forceinline__ void stage_tile(const StageAParams &p, const TileCoord tc, uint8_t *tile) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int px0 = tc.mcu_x0 * 8 * p.hmax, py0 = tc.mcu_y * 8 * VS;
-    const uint8_t *src = p.pixels + (size_t)tc.img * p.image_stride;
-    const size_t row_bytes = (size_t)p.width * BPP;
-    const int valid_px = min(p.tile_w_px, p.width - px0);
-    const int valid_bytes = valid_px * BPP;
-    const int needed_bytes = min(p.tile_w_px, p.mcu_cols * 8 * p.hmax - px0) * BPP; // through the last MCU of the row
-    for (int ry = warp; ry < 8 * VS; ry += n_warps) {
-        const int sy = min(py0 + ry, p.height - 1);
-        const uint8_t *row = src + (size_t)sy * row_bytes + (size_t)px0 * BPP;
-        uint8_t *dst = tile + ry * p.tile_pitch;
-        const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
-        for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
-            if (aligned && cb + 16 <= valid_bytes) {
-                cp_async16(dst + cb, row + cb);
-            } else {
-                for (int b = 0; b < 16; ++b) {
-                    const int byte = cb + b;
-                    const int px = byte / BPP, ch = byte - px * BPP;
-                    dst[cb + b] = row[min(px, valid_px - 1) * BPP + ch];
-                }
-            }
-        }
-    }
-}
-
-// HS x VS = sampling factor of the full-resolution components (luma, K); the others are 1x1.
-// Persistent: each CTA walks tiles t = blockIdx.x, + gridDim.x, ... with two shared-memory buffers,
-// so the cp.async traffic of tile i+1 is in flight while the warps transform tile i.
-template <int CT, int HS, int VS, int NT, int MINB>
-__device__ __forceinline__ void stage_a_fast_body(const StageAParams &p);
-
-template <int CT, int HS, int VS, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) stage_a_fast_kernel(const __grid_constant__ StageAParams p) {
-    stage_a_fast_body<CT, HS, VS, NT, MINB>(p);
-}
-template <int CT, int HS, int VS, int NT, int MINB>
-__device__ __forceinline__ void stage_a_fast_body(const StageAParams &p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int BPP = Fmt<CT>::BPP;
-    constexpr bool SUB = HS * VS > 1;                         // are there subsampled (1x1) components?
-    constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
-    const int pitch = p.tile_pitch;
-    const unsigned tile_bytes = (unsigned)pitch * 8 * VS;
-    const unsigned n_tiles = (unsigned)p.tiles_per_row * p.mcu_rows * p.n_images;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int n_tasks = p.groups * p.tasks_per_group;
-
-    unsigned t = blockIdx.x;
-    if (t < n_tiles) stage_tile<BPP, VS>(p, tile_coord(p, t), smem);
-    cp_async_commit();
-    for (unsigned it = 0; t < n_tiles; t += gridDim.x, ++it) {
-        uint8_t *tile = smem + (it & 1) * tile_bytes;
-        cp_async_wait<0>(); // this thread's share of tile `t` has landed ...
-        __syncthreads();    // ... and so has everybody else's; also: every warp has finished tile t - grid
-        const unsigned nt = t + gridDim.x;
-        if (nt < n_tiles) stage_tile<BPP, VS>(p, tile_coord(p, nt), smem + ((it + 1) & 1) * tile_bytes);
-        cp_async_commit();  // tile t + grid streams in while tile t is transformed: one barrier per tile
-
-        const TileCoord tc = tile_coord(p, t);
-        for (int task = warp; task < n_tasks; task += n_warps) {
-            const int group = task / p.tasks_per_group, slot = task - group * p.tasks_per_group;
-            const int comp = p.task_comp[slot], bv = p.task_v[slot], sub = p.task_h[slot];
-            const bool full = !SUB || comp == 0 || comp == 3;
-            const int H = full ? HS : 1, V = full ? VS : 1;
-            // block column inside the tile's block row of this component, then in the image
-            const int bx_local = (group * H + sub) * 32 + lane;
-            const int bx = tc.mcu_x0 * H + bx_local;
-            if (bx >= p.comp_pw[comp]) continue;
-            const uint8_t *base = full ? tile + (bv * 8) * pitch + bx_local * 8 * BPP : tile + bx_local * 8 * HS * BPP;
-
-            int v[64];
-            if constexpr (CT == JPGB_LUMA) {
-                load_block<CT, ROLE_RAW, 1, 1>(base, pitch, v);
-            } else if constexpr (SUB) {
-                if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
-                else if (comp == 1) load_block<CT, ROLE_CB, HS, VS>(base, pitch, v);
-                else if (NCOMP == 3 || comp == 2) load_block<CT, ROLE_CR, HS, VS>(base, pitch, v);
-                else load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
-            } else {
-                if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, pitch, v);
-                else if (comp == 1) load_block<CT, ROLE_CB, 1, 1>(base, pitch, v);
-                else if (NCOMP == 3 || comp == 2) load_block<CT, ROLE_CR, 1, 1>(base, pitch, v);
-                else load_block<CT, ROLE_K, 1, 1>(base, pitch, v);
-            }
-
-#pragma unroll
-            for (int y = 0; y < 8; ++y)
-                dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
-#pragma unroll
-            for (int x = 0; x < 8; ++x)
-                dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
-
-            const size_t blk = (size_t)tc.img * p.blocks_per_image + p.comp_off[comp] +
-                               (size_t)(tc.mcu_y * V + bv) * p.comp_pw[comp] + bx;
-            int16_t *dst = p.coef + blk * 64;
-            if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
-            else quantize_store256<1>(p, v, dst);
-        }
-    }
-    cp_async_wait<0>();
-}
 
 // Byte-wise fill of one 16-byte chunk with the row's last pixel replicated (Q4). Cold path, kept out of line.
 template <int BPP>
@@ -799,40 +677,9 @@ cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <typename K>
-cudaError_t launch_persistent(K kernel, const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream);
-
-template <int CT, int HS, int VS, int NT, int MINB>
-cudaError_t launch_fast_v(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
-    return launch_persistent(stage_a_fast_kernel<CT, HS, VS, NT, MINB>, p, block, tile_bytes, stream);
-}
-
-template <typename K>
-cudaError_t launch_persistent(K kernel, const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
-    const size_t smem = 2 * tile_bytes;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, n_sms = 0, ctas_per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, (int)block.x, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const unsigned long long n_tiles = (unsigned long long)p.tiles_per_row * p.mcu_rows * p.n_images;
-    unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm; // persistent: one resident wave
-    if (grid > n_tiles) grid = n_tiles;
-    kernel<<<(unsigned)grid, block, smem, stream>>>(p);
-    return cudaGetLastError();
-}
-
 template <int CT, int HS, int VS>
-cudaError_t launch_fast(const StageAParams &p, dim3 block, size_t tile_bytes, cudaStream_t stream) {
-    // Default: the warp-autonomous kernel (measured on B200, C3: 54 % of the HBM peak against 48 % for
-    // the CTA-tile kernel). JPGB_STAGE_A_VARIANT=cta selects the CTA-tile kernel for A/B runs.
-    static const char *v = std::getenv("JPGB_STAGE_A_VARIANT");
-    if (!(v && v[0] == 'c')) return launch_warp_variant<CT, HS, VS>(p, stream);
-    if (block.x <= 192) return launch_fast_v<CT, HS, VS, 192, 2>(p, block, tile_bytes, stream);
-    return launch_fast_v<CT, HS, VS, 256, 2>(p, block, tile_bytes, stream);
+cudaError_t launch_fast(const StageAParams &p, dim3, size_t, cudaStream_t stream) {
+    return launch_warp_variant<CT, HS, VS>(p, stream);
 }
 
 template <int CT>

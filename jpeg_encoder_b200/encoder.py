@@ -200,6 +200,8 @@ def load_library():
     l.jpgb_encoder_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     l.jpgb_encoder_last_launch_count.argtypes = [vp]
     l.jpgb_encoder_last_launch_count.restype = C.c_uint32
+    l.jpgb_build_header.argtypes = [C.POINTER(_Params), u8p, C.c_size_t, C.POINTER(C.c_size_t)]
+    l.jpgb_optimized_huffman_table.argtypes = [C.POINTER(C.c_uint32), u8p, u8p, C.POINTER(C.c_uint32)]
     l.jpgb_version.restype = C.c_char_p
     _lib = l
     return l
@@ -526,6 +528,18 @@ class Encoder:
         if rc != 0:
             self._raise(rc)
         return d_bytes.value, list(offs)
+
+    def build_header(self, width, height, color_type):
+        """SOI .. first SOS as the host planner writes them (default Huffman tables). No GPU needed."""
+        p = self._params(width, height, ColorType(color_type))
+        n = C.c_size_t()
+        lib = load_library()
+        rc = lib.jpgb_build_header(C.byref(p), None, 0, C.byref(n))
+        if rc != 0:
+            raise EncodingError(rc)
+        buf = (C.c_uint8 * n.value)()
+        lib.jpgb_build_header(C.byref(p), buf, n.value, C.byref(n))
+        return bytes(buf)
 
     def coef_layout(self, width, height, color_type):
         p = self._params(width, height, ColorType(color_type))

@@ -120,3 +120,67 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     if not torch.cuda.is_available():
         assert "EncodingError 8" in r.stdout  # JPGB_ERR_CUDA: no fallback
+
+
+# ---- host planner against the oracle, no GPU -----------------------------------------------------
+def _first_scan_data_offset(jpg):
+    """offset just past the first SOS segment"""
+    i = 2
+    while True:
+        assert jpg[i] == 0xFF
+        m = jpg[i + 1]
+        n = int.from_bytes(jpg[i + 2:i + 4], "big")
+        i += 2 + n
+        if m == 0xDA:
+            return i
+
+
+@pytest.mark.parametrize("color", ["luma", "rgb", "bgra", "ycbcr", "cmyk", "cmyk_as_ycck", "ycck"])
+def test_header_bytes_match_oracle(color):
+    """Container segments written by the C++ planner (csrc/host.cpp) == the oracle's, for every mode that
+    uses the default Huffman tables (Q10 truncated DQT, Q11 component ids, Q21 segment order, DRI, APPn)."""
+    import numpy as np
+    from cases import BPP, CT, make_encoder, oracle_encode
+    rng = np.random.default_rng(1)
+    big = rng.integers(1, 3000, 64).tolist()
+    cfgs = [dict(quality=90, sampling=(2, 2)), dict(quality=30, sampling=(4, 1), restart_interval=77),
+            dict(quality=100, sampling=(1, 2), progressive_scans=7), dict(quality=55, qtables=(big, 3), sampling=(2, 4)),
+            dict(quality=75, density=(1, 300, 72), app_segments=[(1, b"Exif\0\0abc"), (15, bytes(range(200)))], progressive_scans=2,
+                 restart_interval=1)]
+    w, h = 37, 21
+    img = rng.integers(0, 256, (h, w, BPP[color]), dtype=np.uint8)
+    for cfg in cfgs:
+        want = oracle_encode(img if BPP[color] > 1 else img[..., 0], w, h, color, cfg)
+        got = make_encoder(cfg).build_header(w, h, CT[color][1])
+        assert got == want[:_first_scan_data_offset(want)], cfg
+
+
+def test_optimized_huffman_host_matches_oracle():
+    """Annex K.2 as run by the planner == the oracle's restatement, on skewed, flat and sparse histograms."""
+    import numpy as np
+    from oracle import oracle as orc
+    lib = je.load_library()
+    rng = np.random.default_rng(2)
+    cases = []
+    for _ in range(40):
+        f = np.zeros(257, np.uint32)
+        k = int(rng.integers(1, 257))
+        idx = rng.choice(256, k, replace=False)
+        f[idx] = (rng.pareto(0.7, k) * 10 + 1).astype(np.uint32) if rng.random() < 0.7 else rng.integers(1, 50, k)
+        f[256] = 1
+        cases.append(f)
+    fib = np.zeros(257, np.uint32)  # Fibonacci-like frequencies force the > 16 bit length limiting of Figure K.3
+    a, b = 1, 1
+    for i in range(30):
+        fib[i] = a
+        a, b = b, a + b
+    fib[256] = 1
+    cases.append(fib)
+    for f in cases:
+        length = (C.c_uint8 * 16)()
+        values = (C.c_uint8 * 256)()
+        n = C.c_uint32()
+        rc = lib.jpgb_optimized_huffman_table(f.ctypes.data_as(C.POINTER(C.c_uint32)), length, values, C.byref(n))
+        assert rc == 0
+        want_len, want_vals = orc.huffman_optimized(f.tolist())
+        assert list(length) == want_len and list(values)[:n.value] == want_vals

@@ -66,20 +66,6 @@ def test_generic_and_fast_stage_a_kernels_agree(monkeypatch):
         monkeypatch.setenv("JPGB_FORCE_GENERIC_STAGE_A", "1")
         assert gpu_encode(img, 333, 77, color, cfg) == want
         monkeypatch.delenv("JPGB_FORCE_GENERIC_STAGE_A")
-    # the CTA-tile variant of the fast kernel is chosen once per process (static): exercised in a subprocess
-    import subprocess
-    import sys
-    code = ("import sys; sys.path.insert(0, 'tests'); import images; from cases import gpu_encode, oracle_encode\n"
-            "for c, s in (('rgb', (2, 2)), ('luma', (1, 1)), ('cmyk_as_ycck', (1, 1)), ('bgra', (2, 1)), ('rgb', (1, 1))):\n"
-            "    ch = {'rgb': 3, 'luma': 1, 'cmyk_as_ycck': 4, 'bgra': 4}[c]\n"
-            "    img = images.photo_like(333, 77, ch, seed=5); cfg = dict(quality=83, sampling=s)\n"
-            "    assert gpu_encode(img, 333, 77, c, cfg) == oracle_encode(img, 333, 77, c, cfg), (c, s)\n"
-            "print('cta variant ok')")
-    import os
-    env = dict(os.environ, JPGB_STAGE_A_VARIANT="cta")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
-    assert r.returncode == 0 and "cta variant ok" in r.stdout, r.stdout + r.stderr
 
 
 # ---- the reference's own end-to-end cases (src/lib.rs:188-553), now compared on bytes -----------
