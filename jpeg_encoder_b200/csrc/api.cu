@@ -71,7 +71,8 @@ struct jpgb_encoder {
     bool own_stream = false;
     std::string err;
     DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
-        scan_tmp, hist, piece_off, out2, pixels2, status;
+        scan_tmp, hist, piece_off, out2, pixels2, status, scan_err;
+    std::vector<uint8_t> last_plan, last_tables; // what the device currently holds
     double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
     PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out;
     int out_slot = 0; // which of out / out2 the next encode_device writes
@@ -163,7 +164,12 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 
     CK(enc->coef.reserve(n_blocks * 128), "alloc coefficients");
     CK(enc->plan.reserve(sizeof(DevPlan)), "alloc plan");
-    CK(cudaMemcpyAsync(enc->plan.p, &hp, sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
+    // repeated calls with the same settings skip the small uploads (the device copies are still valid)
+    if (enc->last_plan.size() != sizeof(DevPlan) || std::memcmp(enc->last_plan.data(), &hp, sizeof(DevPlan)) != 0) {
+        enc->last_plan.assign(reinterpret_cast<const uint8_t *>(&hp), reinterpret_cast<const uint8_t *>(&hp) + sizeof(DevPlan));
+        CK(cudaMemcpyAsync(enc->plan.p, enc->last_plan.data(), sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
+        CK(cudaStreamSynchronize(st), "plan upload sync"); // pageable source: keep it simple and rare
+    }
 
     // ---- stage A ----
     {
@@ -224,9 +230,13 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         CK(enc->huff.reserve(tab_bytes), "alloc huffman tables");
         CK(enc->hdr.reserve(hdr_bytes), "alloc headers");
         CK(enc->hdr_len.reserve(len_bytes), "alloc header lengths");
-        CK(cudaMemcpyAsync(enc->huff.p, hb, tab_bytes, cudaMemcpyHostToDevice, st), "upload huffman tables");
-        CK(cudaMemcpyAsync(enc->hdr.p, hb + tab_bytes, hdr_bytes, cudaMemcpyHostToDevice, st), "upload headers");
-        CK(cudaMemcpyAsync(enc->hdr_len.p, hb + tab_bytes + hdr_bytes, len_bytes, cudaMemcpyHostToDevice, st), "upload header lengths");
+        const size_t blob = tab_bytes + hdr_bytes + len_bytes;
+        if (enc->last_tables.size() != blob || std::memcmp(enc->last_tables.data(), hb, blob) != 0) {
+            enc->last_tables.assign(hb, hb + blob);
+            CK(cudaMemcpyAsync(enc->huff.p, hb, tab_bytes, cudaMemcpyHostToDevice, st), "upload huffman tables");
+            CK(cudaMemcpyAsync(enc->hdr.p, hb + tab_bytes, hdr_bytes, cudaMemcpyHostToDevice, st), "upload headers");
+            CK(cudaMemcpyAsync(enc->hdr_len.p, hb + tab_bytes + hdr_bytes, len_bytes, cudaMemcpyHostToDevice, st), "upload header lengths");
+        }
     }
 
     // ---- symbol sizing and the two prefix sums ----
@@ -252,12 +262,16 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     b.hdr_stride = (uint32_t)hdr_stride;
     b.scan_tmp = enc->scan_tmp.p;
 
+    CK(enc->status.reserve(64), "alloc status");
+    CK(enc->scan_err.reserve(8), "alloc scan flag");
+    CK(cudaMemsetAsync(enc->scan_err.p, 0, 8, st), "clear scan flag");
+    unsigned long long *scan_err = enc->scan_err.as<unsigned long long>();
     {
         StageTimer t(enc, 2);
         CK(launch_symbol_sizes(b, hp, n, st), "symbol size launch");
-        CK(launch_exclusive_scan(b.nbits, b.bitpos, n_visits, b.scan_tmp, st, &enc->launches), "bit position scan");
+        CK(launch_exclusive_scan(b.nbits, b.bitpos, n_visits, b.scan_tmp, st, &enc->launches, scan_err), "bit position scan");
         CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
-        CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches), "segment position scan");
+        CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches, scan_err), "segment position scan");
         enc->launches += 2;
     }
 
@@ -272,7 +286,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     uint64_t ocap = ucap + ucap / 32 + 4096;
     uint64_t ubytes = 0, total = 0;
     CK(enc->file_off.reserve((size_t)(n + 1) * 8), "alloc file offsets");
-    CK(enc->status.reserve(32), "alloc status");
     CK(enc->h_small.reserve(64 + (size_t)(n + 1) * 8), "alloc readback");
     b.file_off = enc->file_off.as<unsigned long long>();
     b.status = enc->status.as<unsigned long long>();
@@ -306,7 +319,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         {
             StageTimer t(enc, 4);
             CK(launch_count_ff(b, st), "count ff launch");
-            CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches), "ff scan");
+            CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "ff scan");
             CK(launch_stuff_scatter(b, st), "scatter launch");
             CK(launch_file_offsets(b, hp, n, st), "file offsets launch");
             enc->launches += 3;
@@ -319,10 +332,12 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
                 CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
             }
             CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 32, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
-            CK(cudaMemcpyAsync(enc->h_small.p, b.status, 32, cudaMemcpyDeviceToHost, st), "read status");
+            CK(cudaMemcpyAsync(enc->h_small.p, b.status, 24, cudaMemcpyDeviceToHost, st), "read status");
+            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 24, scan_err, 8, cudaMemcpyDeviceToHost, st), "read scan flag");
         }
         CK(cudaStreamSynchronize(st), "final sync");
         const uint64_t *status = enc->h_small.as<uint64_t>();
+        if (status[3]) return fail(enc, JPGB_ERR_CUDA, "internal: prefix-sum look-back timed out");
         ubytes = status[0];
         if (status[2] == 0) {
             total = ubytes + status[1];
@@ -508,7 +523,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
-                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status};
+                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status, &e->scan_err};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
     e->h_hist.release();

@@ -39,7 +39,7 @@ struct EntropyBuffers {
     // capacities (bytes) of ustream / out and the status block the kernels report into: the host sizes the
     // buffers from the previous call and checks `status` once at the end instead of syncing mid-pipeline
     unsigned long long ustream_cap, out_cap, n_segs_total;
-    unsigned long long *status;    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out)
+    unsigned long long *status;    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out), [3] scan error
     size_t scan_tmp_bytes;
 };
 
@@ -64,6 +64,6 @@ cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, u
 // scan.cu -- device-wide exclusive prefix sum of u32 into u64; out has n + 1 entries (out[n] = total)
 size_t scan_tmp_bytes(uint64_t n);
 cudaError_t launch_exclusive_scan(const uint32_t *in, unsigned long long *out, uint64_t n, void *tmp, cudaStream_t stream,
-                                  uint32_t *launches);
+                                  uint32_t *launches, unsigned long long *err_flag = nullptr);
 
 } // namespace jpgb

@@ -658,14 +658,19 @@ cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     constexpr int TILE = 256 * BPP * 8 * VS * MR;
     const size_t smem = (size_t)4 * TILE + 4 * sizeof(uint64_t); // 4 warps per CTA: one private tile and one mbarrier each
     auto kernel = stage_a_warp_kernel<CT, HS, VS>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, n_sms = 0, ctas_per_sm = 0;
+    // per device, once: opt in to the dynamic shared memory and ask how many CTAs fit on an SM
+    static int cached_dev = -1, n_sms = 0, ctas_per_sm = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 128, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (dev != cached_dev) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        cached_dev = dev;
+    }
     constexpr int MCUS = 32 / HS;
     const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * ((p.mcu_rows + MR - 1) / MR) * p.n_images;
     unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm;
