@@ -369,3 +369,34 @@ def test_encode_planes_all_jpeg_color_types(kind):
         # the packed adaptors copy Luma/Ycbcr/Ycck samples verbatim and invert Cmyk (src/image_buffer.rs:115-121, 221-229, 247-256, 303-312)
         ref_in = 255 - packed if kind == "cmyk" else packed
         assert got == oracle_encode(ref_in, w, h, kind, cfg)
+
+
+def test_concurrent_contexts_on_threads():
+    """One jpgb_encoder context per host thread (the reference's Encoder is Send, not shared): four threads
+    encode different configurations at the same time on their own streams; every result must stay exact."""
+    import threading
+    import jpeg_encoder_b200 as je
+    cfgs = [("rgb", dict(quality=90, sampling=(2, 2))), ("luma", dict(quality=70, progressive_scans=3)),
+            ("cmyk_as_ycck", dict(quality=85, sampling=(1, 1), optimize_huffman=True)), ("bgr", dict(quality=60, sampling=(2, 1), restart_interval=5))]
+    imgs = [_img(c, 640, 360, seed=40 + i) for i, (c, _) in enumerate(cfgs)]
+    want = [oracle_encode(imgs[i], 640, 360, c, cfg) for i, (c, cfg) in enumerate(cfgs)]
+    errors = []
+
+    def work(i):
+        try:
+            dev = je.Device(0)
+            color, cfg = cfgs[i]
+            for _ in range(12):
+                if make_encoder(cfg, dev).encode(imgs[i], 640, 360, CT[color][1]) != want[i]:
+                    errors.append("thread %d: bytes differ" % i)
+                    break
+            dev.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append("thread %d: %r" % (i, e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
