@@ -3,7 +3,7 @@
 * Batches shard by image: rank r owns images [lo, hi) -- no data-path collective at all.
 * One very large image shards by strips of whole MCU rows whose boundaries are restart boundaries
   of every scan. Each rank encodes its strip; the only exchange is the gather of the strips'
-  per-scan byte pieces to rank 0 (sizes first, then one variable-length send per rank over
+  per-scan byte pieces to rank 0 (sizes first, then one grouped batch of variable-length sends over
   NCCL/NVLink), where they are concatenated scan-major.
 
 The exchange functions work on whatever device the tensors live on: NCCL with CUDA tensors on the
@@ -39,23 +39,22 @@ def split_pieces(buf, offsets):
 def gather_strip_pieces(local_bytes, piece_offsets, rank, world, device, group=None):
     """local_bytes: uint8 tensor on `device` holding this rank's pieces back to back.
     Returns on rank 0 the assembled uint8 tensor of the whole file (scan-major), on other ranks None.
-    Communication: one all_gather of the (n_scans + 1) offsets, then ONE gather of the byte buffers to
-    rank 0 (padded to the longest; NCCL runs it as a single grouped send/recv over NVLink)."""
+    Communication: one all_gather of the (n_scans + 1) offsets, then one batch of point-to-point
+    transfers into rank 0 (a single grouped NCCL send/recv over NVLink; exact sizes, no padding)."""
     n = len(piece_offsets)
     mine = torch.tensor(piece_offsets, dtype=torch.int64, device=device)
     table = torch.empty(world * n, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(table, mine, group=group)
     table = table.cpu().view(world, n).tolist()
-    longest = max(t[-1] for t in table)
-    send = local_bytes
-    if send.numel() < longest:  # pad (the context's buffer is usually larger than the file already)
-        send = torch.empty(longest, dtype=torch.uint8, device=device)
-        send[:local_bytes.numel()].copy_(local_bytes)
-    send = send[:longest]
     if rank == 0:
-        bufs = [torch.empty(longest, dtype=torch.uint8, device=device) for _ in range(world)]
-        dist.gather(send, bufs, dst=0, group=group)
+        bufs = [local_bytes] + [torch.empty(table[r][-1], dtype=torch.uint8, device=device) for r in range(1, world)]
+        ops = [dist.P2POp(dist.irecv, bufs[r], r, group) for r in range(1, world) if table[r][-1] > 0]
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         parts = [bufs[r][table[r][k]:table[r][k + 1]] for k in range(n - 1) for r in range(world)]
         return torch.cat(parts)
-    dist.gather(send, None, dst=0, group=group)
+    if piece_offsets[-1] > 0:
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_bytes[:piece_offsets[-1]], 0, group)]):
+            q.wait()
     return None
