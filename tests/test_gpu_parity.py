@@ -28,6 +28,19 @@ def _same(color, w, h, cfg, img=None, seed=1):
     return got
 
 
+# ---- committed fixtures: no oracle code runs in this test ----------------------------------------
+def test_committed_file_hashes():
+    """GPU file bytes against tests/golden/oracle_jpegs.json (SHA-256 written by make_golden.py in the build container)."""
+    import hashlib, json, os, sys
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gold)
+    import make_golden
+    want = json.load(open(os.path.join(gold, "oracle_jpegs.json")))
+    for name, maker, size, color, cfg in make_golden.golden_matrix():
+        data = gpu_encode(getattr(images, maker)(*size), size[0], size[1], color, cfg)
+        assert (hashlib.sha256(data).hexdigest(), len(data)) == (want[name]["sha256"], want[name]["len"]), name
+
+
 # ---- stage A on its own: coefficients bit-exact --------------------------------------------------
 @pytest.mark.parametrize("color,sampling", [("rgb", (2, 2)), ("rgb", (1, 1)), ("rgb", (4, 1)), ("rgb", (2, 4)), ("luma", (1, 1)),
                                             ("cmyk_as_ycck", (1, 1)), ("cmyk", (2, 2)), ("bgra", (2, 1)), ("ycck", (1, 2))])

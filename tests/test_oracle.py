@@ -15,6 +15,25 @@ from oracle import oracle as orc
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+# ---- committed file hashes (tests/golden/make_golden.py) ---------------------------------------
+def _golden():
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden
+    return make_golden, json.load(open(os.path.join(GOLD, "oracle_jpegs.json")))
+
+
+def test_oracle_reproduces_committed_file_hashes():
+    """The oracle's file bytes for the fixed configuration matrix have not drifted since they were committed."""
+    import hashlib
+    mg, want = _golden()
+    cases = mg.golden_matrix()
+    assert sorted(c[0] for c in cases) == sorted(want)
+    for case in cases:
+        data = mg.encode_case(case)
+        assert (hashlib.sha256(data).hexdigest(), len(data)) == (want[case[0]]["sha256"], want[case[0]]["len"]), case[0]
+
+
 # ---- unit known-answer tests ------------------------------------------------------------------
 def test_rgb_to_ycbcr_kat():
     """src/image_buffer.rs:325-422 (5 primaries + 88 libjpeg-derived triples)."""
