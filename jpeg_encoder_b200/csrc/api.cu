@@ -223,7 +223,9 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         CK(enc->h_tables.reserve(tab_bytes + hdr_bytes + len_bytes), "alloc tables (host)");
         uint8_t *hb = enc->h_tables.as<uint8_t>();
         for (uint32_t i = 0; i < n_huff; ++i) {
-            for (int t = 0; t < 4; ++t) std::memcpy(hb + ((size_t)i * 4 + t) * 1024, tables[i * 4 + t].lookup, 1024);
+            for (int t = 0; t < 4; ++t) // [table][dc, ac]
+                if (!tables[i * 4 + t].device_words(t & 1, reinterpret_cast<uint32_t *>(hb + ((size_t)i * 4 + t) * 1024)))
+                    return fail(enc, JPGB_ERR_HUFFMAN, "a Huffman code plus its value bits exceeds 31 bits");
             std::memcpy(hb + tab_bytes + (size_t)i * hdr_stride, headers[i].data(), headers[i].size());
             reinterpret_cast<uint32_t *>(hb + tab_bytes + hdr_bytes)[i] = (uint32_t)headers[i].size();
         }
@@ -241,7 +243,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 
     // ---- symbol sizing and the two prefix sums ----
     CK(enc->nbits.reserve(n_visits * 4), "alloc nbits");
-    CK(enc->slots.reserve(n_visits * 4 * kSlotWords), "alloc code slots");
+    CK(enc->slots.reserve((n_visits + kSlotTile - 1) / kSlotTile * kSlotTile * 4 * kSlotWords), "alloc code slots");
     CK(enc->bitpos.reserve((n_visits + 1) * 8), "alloc bitpos");
     CK(enc->seglen.reserve(n_segs * 4), "alloc seglen");
     CK(enc->segpos.reserve((n_segs + 1) * 8), "alloc segpos");

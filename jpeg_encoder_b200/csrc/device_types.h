@@ -7,6 +7,28 @@ namespace jpgb {
 constexpr int kMaxScans = 256;  // 4 components x 64 progressive scans
 constexpr int kMaxSlots = 20;   // blocks per MCU-sized unit: YCCK at F_4_2 / F_2_4 has 8 + 1 + 1 + 8 = 18
 
+// n / d for 32-bit n and a divisor fixed per launch: one multiply-high and one correction step instead of the
+// ~20-instruction divide. m = floor(2^32 / d) (2^32 - 1 for d = 1) under-estimates the quotient by at most one.
+struct FastDiv {
+    unsigned d, m;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    f.m = d <= 1 ? 0xFFFFFFFFu : (unsigned)((1ull << 32) / d);
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void divmod(unsigned n, const FastDiv f, unsigned &q, unsigned &r) {
+    q = __umulhi(n, f.m);
+    r = n - q * f.d;
+    if (r >= f.d) {
+        ++q;
+        r -= f.d;
+    }
+}
+#endif
+
 // Quantizer constants per table, natural order. q = (v*mul + (v < 0 ? add_neg : add_pos)) >> 16
 // reproduces `((abs(v) + corr) * recip) >> 15` with the sign re-applied (src/quantization.rs:291-307):
 // mul = 2*recip, add_pos = 2*corr*recip, add_neg = 2*(32767 - corr*recip).
@@ -42,6 +64,7 @@ struct StageAParams {
 struct DevScan {
     int comp, ss, se;
     unsigned n_units, bpu;
+    FastDiv div_bpu;
     unsigned long long visit_base;
     unsigned seg_base, n_segs;
     unsigned sos_off, sos_len;  // into DevPlan::blob
@@ -57,6 +80,7 @@ struct DevPlan {
     int8_t slot_comp[kMaxSlots], slot_v[kMaxSlots], slot_h[kMaxSlots];
     int comp_h[4], comp_v[4], comp_tbl[4];
     unsigned comp_pw[4], comp_tw[4];   // padded / true blocks per row
+    FastDiv div_tw[4], div_mcu_cols, div_restart, div_vpi; // div_vpi.d == 0: visits_per_image needs 64 bits
     unsigned long long comp_off[4];
     DevScan scans[kMaxScans];
     unsigned char blob[kMaxScans * 10]; // SOS segments of scans 1.. (10 bytes each: single component)

@@ -58,13 +58,14 @@ __device__ __forceinline__ int find_scan_by_seg(const DevPlan &P, unsigned s) {
     return lo;
 }
 
-// g = img * visits_per_image + v. 64-bit division is ~100 instructions on the GPU; nearly every call has
-// both numbers below 2^32, where the 32-bit divide is a handful.
+// g = img * visits_per_image + v. Nearly every call has both numbers below 2^32 (FastDiv); the 64-bit
+// divide is ~100 instructions.
 __device__ __forceinline__ void split_visit(const DevPlan &P, unsigned long long g, unsigned long long &img, unsigned long long &v) {
-    if ((g >> 32) == 0 && (P.visits_per_image >> 32) == 0) {
-        const unsigned q = (unsigned)g / (unsigned)P.visits_per_image;
+    if ((g >> 32) == 0 && P.div_vpi.d != 0) {
+        unsigned q, r;
+        divmod((unsigned)g, P.div_vpi, q, r);
         img = q;
-        v = (unsigned)g - q * (unsigned)P.visits_per_image;
+        v = r;
     } else {
         img = g / P.visits_per_image;
         v = g - img * P.visits_per_image;
@@ -77,8 +78,7 @@ __device__ __forceinline__ void split_unit(const DevScan &S, unsigned long long 
         unit = rel;
         slot = 0;
     } else {
-        unit = rel / S.bpu;
-        slot = rel - unit * S.bpu;
+        divmod(rel, S.div_bpu, unit, slot);
     }
 }
 
@@ -93,7 +93,8 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
     unsigned unit, slot;
     split_unit(S, v, unit, slot);
     const unsigned R = (unsigned)P.restart;
-    const unsigned seg_q = R ? unit / R : 0, seg_r = R ? unit - seg_q * R : unit; // unit = seg_q * R + seg_r
+    unsigned seg_q = 0, seg_r = unit; // unit = seg_q * R + seg_r
+    if (R) divmod(unit, P.div_restart, seg_q, seg_r);
     const bool restart_here = unit == 0 || (R && seg_r == 0);
     unsigned long long blk, pred = 0;
     bool has_pred = true;
@@ -102,25 +103,27 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
         comp = P.slot_comp[slot];
         const unsigned bv = P.slot_v[slot], bh = P.slot_h[slot];
         const unsigned H = P.comp_h[comp], V = P.comp_v[comp], pw = P.comp_pw[comp];
-        const unsigned my = unit / P.mcu_cols, mx = unit - my * P.mcu_cols;
+        unsigned my, mx;
+        divmod(unit, P.div_mcu_cols, my, mx);
         const unsigned long long off = P.comp_off[comp];
         blk = off + (unsigned long long)(my * V + bv) * pw + mx * H + bh;
         if (bh > 0) pred = blk - 1;
         else if (bv > 0) pred = off + (unsigned long long)(my * V + bv - 1) * pw + mx * H + (H - 1);
         else if (restart_here) has_pred = false;
-        else {
-            const unsigned pu = unit - 1, pmy = pu / P.mcu_cols, pmx = pu - pmy * P.mcu_cols;
+        else { // last block of this component in the previous MCU
+            const unsigned pmy = mx ? my : my - 1, pmx = mx ? mx - 1 : P.mcu_cols - 1;
             pred = off + (unsigned long long)(pmy * V + V - 1) * pw + pmx * H + (H - 1);
         }
     } else {
         comp = S.comp;
         const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
         const unsigned long long off = P.comp_off[comp];
-        const unsigned by = unit / tw, bx = unit - by * tw;
+        unsigned by, bx;
+        divmod(unit, P.div_tw[comp], by, bx);
         blk = off + (unsigned long long)by * pw + bx;
         if (restart_here) has_pred = false;
-        else {
-            const unsigned pu = unit - 1, pby = pu / tw, pbx = pu - pby * tw;
+        else { // previous block of the raster grid
+            const unsigned pby = bx ? by : by - 1, pbx = bx ? bx - 1 : tw - 1;
             pred = off + (unsigned long long)pby * pw + pbx;
         }
     }
@@ -141,121 +144,272 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
 // get_code, writer.rs:455-470: size = bit length of |v|, bits = low `size` bits of (v - (v<0))
 __device__ __forceinline__ void value_code(int v, int &size, uint32_t &bits) {
     const int a = v < 0 ? -v : v;
-    size = 32 - __clz(a);
-    bits = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << size) - 1u);
+    int top; // index of the highest set bit, -1 for 0
+    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(a));
+    size = top + 1;
+    bits = (uint32_t)(v + (v >> 31)) & ~(~0u << size);
 }
 
-// Bit sink of one visit. Codes are packed MSB-first into 32-bit words; word j of visit g goes to
-// slots[j * stride + g] (word-major: the lanes of a warp, which flush word j at about the same time,
-// write one contiguous line). The visit is coded exactly once; where its bits belong in the stream is
-// decided later, from the prefix sum of `total`, by place_bits_kernel.
+__device__ __forceinline__ unsigned nonzero16x2(unsigned x) {
+    unsigned r;
+    asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(0x00010001u));
+    return r;
+}
+
+// Bit sink of one visit. Codes are packed MSB-first into 32-bit words. Slots are tiled by kSlotTile
+// visits (one coding CTA): word j of visit g lives at slot_of(g)[j * kSlotTile], so the lanes of a warp
+// write one contiguous line per word and a CTA's slots are one contiguous 56 KB region. (Word-major
+// across the whole launch, planes n_visits words apart, made every CTA touch a dozen pages hundreds of
+// MB apart and the coding kernel TLB-bound.) The visit is coded exactly once; where its bits belong in
+// the stream is decided later, from the prefix sum of the totals, by place_bits_kernel.
+__device__ __forceinline__ uint32_t *slot_of(uint32_t *slots, unsigned long long g) {
+    return slots + (g / kSlotTile) * (kSlotTile * kSlotWords) + (g % kSlotTile);
+}
+
 struct BitSink {
-    unsigned total = 0;
     unsigned long long acc = 0;
     int n = 0;
+    unsigned words = 0;
     uint32_t *slot;
-    unsigned long long stride;
 
-    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long stride_, unsigned long long g)
-        : slot(slots + g), stride(stride_) {}
-    __device__ __forceinline__ void put(uint32_t code, int len) {
-        total += len;
+    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long g) : slot(slot_of(slots, g)) {}
+    __device__ __forceinline__ void put(uint32_t code, int len) { // len <= 31, n < 32 on entry
         acc = (acc << len) | code;
         n += len;
         if (n >= 32) {
             *slot = (uint32_t)(acc >> (n - 32));
-            slot += stride;
+            slot += kSlotTile;
             n -= 32;
+            ++words;
         }
     }
-    __device__ __forceinline__ void finish() {
+    __device__ __forceinline__ unsigned finish() {
         if (n > 0) *slot = (uint32_t)(acc << (32 - n)); // left-aligned tail
+        return words * 32 + n;
     }
 };
 
-// write_dc + write_ac_block restricted to [ss, se] for one visit (writer.rs:342-388).
-// A symbol without a code has lookup 0: only the value bits are written (release-build behaviour
-// of the reference).
-// FULL: the scan covers the whole block (ss = 0, se = 63: baseline and sequential scans), so the
-// per-coefficient band checks vanish. Groups of 8 and pairs of coefficients that are all zero only
-// extend the current zero run.
-template <bool FULL>
-__device__ __forceinline__ void code_visit(const VisitInfo &vi, const uint32_t *__restrict__ dc_tab,
-                                           const uint32_t *__restrict__ ac_tab, BitSink &sink) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(vi.blk);
-    int run = 0;
-    const int ss = FULL ? 0 : vi.ss, se = FULL ? 63 : vi.se;
-    const int first_ac = ss == 0 ? 1 : ss;
-    const int w_lo = se == 0 ? 0 : first_ac >> 3, w_hi = se >> 3;
-    uint4 q = __ldg(src + w_lo);
-    if (ss == 0) {
-        const int dc = (int)(int16_t)(q.x & 0xFFFFu); // w_lo == 0 whenever ss == 0
-        const int prev = vi.pred ? (int)vi.pred[0] : 0;
-        const int diff = (int)(int16_t)(dc - prev);
-        int size;
-        uint32_t bits;
-        value_code(diff, size, bits);
-        const uint32_t h = __ldg(dc_tab + size);
-        sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
-    }
-    if (se == 0) return;
-    const uint32_t zrl = __ldg(ac_tab + 0xF0);
-    for (int w = w_lo; w <= w_hi; ++w) {
-        const uint4 nxt = w < w_hi ? __ldg(src + w + 1) : q; // prefetch the next group
-        const bool edge = w == 0 || (!FULL && (w == w_lo || w == w_hi));
-        if (!edge && (q.x | q.y | q.z | q.w) == 0) {
-            run += 8;
-        } else {
-            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!edge && words[i] == 0) {
-                    run += 2;
-                    continue;
-                }
-#pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    const int k = w * 8 + 2 * i + hlf;
-                    if (FULL ? k == 0 : (k < first_ac || k > se)) continue;
-                    const int c = (int)(int16_t)(words[i] >> (hlf * 16));
-                    if (c == 0) {
-                        ++run;
-                    } else {
-                        for (; run > 15; run -= 16) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));
-                        int size;
-                        uint32_t bits;
-                        value_code(c, size, bits);
-                        const uint32_t h = __ldg(ac_tab + ((run << 4) | size));
-                        sink.put(((h & 0xFFFFu) << size) | bits, (int)(h >> 16) + size);
-                        run = 0;
-                    }
-                }
-            }
-        }
-        q = nxt;
-    }
-    if (run > 0) { // the band ends in zeros: EOB (writer.rs:383-385)
-        const uint32_t e = __ldg(ac_tab);
-        sink.put(e & 0xFFFFu, (int)(e >> 16));
-    }
-}
+// Table words as the host uploads them (api.cu): for the symbol (run << 4 | size), or the DC category
+// `size`, (code_length + size) << 27 | code << size: OR-ing the value bits in gives the whole
+// write_bits argument of huffman_encode_value (writer.rs:320-329). A symbol without a code is
+// size << 27: only the value bits are written (release-build behaviour of the reference).
+constexpr uint32_t kCodeBits = 0x07FFFFFFu;
+
+constexpr int kEncThreads = kSlotTile;
+constexpr int kStageStride = 72; // int16 per staged block: 128 B of coefficients + 16 B pad (128-bit rows stay conflict-free)
+
+struct __align__(16) EncodeShared {
+    int16_t coef[kEncThreads * kStageStride]; // the CTA's blocks, staged with coalesced loads
+    unsigned long long ptr_or_mask[kEncThreads]; // first the block address | group range, then the non-zero mask
+    uint32_t first[kEncThreads];  // the DC code of the visit (table-word format), 0 in AC scans
+    uint32_t info[kEncThreads];   // se | first_ac << 8 | table << 16 | valid << 24
+    uint32_t ac_tab[2 * 256];
+    uint32_t bin[64];
+    uint16_t order[kEncThreads];
+};
 
 __device__ __forceinline__ const uint32_t *huff_for(const EntropyBuffers &b, unsigned long long img, int tbl, int cls) {
     return b.huff + (b.huff_per_image ? img * kHuffWordsPerImage : 0) + (size_t)(tbl * 2 + cls) * 256;
 }
 
-__global__ void __launch_bounds__(256) encode_visits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_visits) return;
+// write_ac_block restricted to the band (writer.rs:354-388) for one visit whose non-zero positions are
+// the set bits of `lo`/`hi`: one iteration per non-zero coefficient.
+__device__ __forceinline__ void code_nonzeros(unsigned lo, unsigned hi, int first_ac, int se, const int16_t *__restrict__ c,
+                                              const uint32_t *__restrict__ tab, BitSink &sink) {
+    int next = first_ac; // first position of the current zero run
+    int base = -1, k = 0, cv = 0;
+    // the position and value of the following non-zero are fetched while the current one is coded
+    auto advance = [&]() -> bool {
+        if (lo == 0) {
+            lo = hi;
+            hi = 0;
+            base = 31;
+        }
+        if (lo == 0) return false;
+        k = base + __ffs((int)lo);
+        lo &= lo - 1;
+        cv = c[k];
+        return true;
+    };
+    bool more = advance();
+    while (more) {
+        const int kc = k, cc = cv;
+        more = advance();
+        int run = kc - next;
+        next = kc + 1;
+        if (run > 15) {
+            const uint32_t zrl = tab[0xF0];
+#pragma unroll 1
+            do {
+                sink.put(zrl & kCodeBits, (int)(zrl >> 27));
+                run -= 16;
+            } while (run > 15);
+        }
+        int size;
+        uint32_t bits;
+        value_code(cc, size, bits);
+        const uint32_t e = tab[(run << 4) | size];
+        sink.put((e & kCodeBits) | bits, (int)(e >> 27));
+    }
+    if (next <= se) { // the band ends in zeros: EOB (writer.rs:383-385)
+        const uint32_t e = tab[0];
+        sink.put(e & kCodeBits, (int)(e >> 27));
+    }
+}
+
+// write_dc + write_ac_block for 256 consecutive visits per CTA, in three steps:
+//  1. every thread locates its visit; each warp copies its 32 blocks into shared memory with
+//     coalesced 128-bit loads (8 lanes per block);
+//  2. every thread builds the 64-bit mask of non-zero coefficients of its block inside the scan's band
+//     and the DC code; the CTA sorts its visits by their number of non-zeros (counting sort);
+//  3. thread t codes the visit of rank t: the lanes of a warp then run nearly the same number of
+//     iterations of the per-coefficient loop, which is where the time goes.
+// FULL: every scan of the plan covers the whole block (baseline and sequential modes), so the band
+// bookkeeping is constant.
+template <bool FULL>
+__global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
+    __shared__ EncodeShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long cta_base = (unsigned long long)blockIdx.x * kEncThreads;
+    const unsigned long long g = cta_base + tid;
+    const bool valid = g < n_visits;
     const DevPlan &P = *b.plan;
-    unsigned long long img, v;
-    split_visit(P, g, img, v);
-    const VisitInfo vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
-    BitSink sink(b.slots, n_visits, g);
-    if (vi.ss == 0 && vi.se == 63) code_visit<true>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
-    else code_visit<false>(vi, huff_for(b, img, vi.tbl, 0), huff_for(b, img, vi.tbl, 1), sink);
-    sink.finish();
-    b.nbits[g] = sink.total;
+
+    // AC tables of the CTA's first image into shared memory; a CTA that spans images with their own
+    // (optimized) tables reads them from global memory instead
+    unsigned long long img_first = 0, img_last = 0, tmp;
+    if (b.huff_per_image) {
+        split_visit(P, cta_base, img_first, tmp);
+        split_visit(P, (cta_base + kEncThreads < n_visits ? cta_base + kEncThreads : n_visits) - 1, img_last, tmp);
+    }
+    const bool shared_tables = img_first == img_last;
+    if (shared_tables) {
+        const uint32_t *set = b.huff + img_first * kHuffWordsPerImage;
+        for (int i = tid; i < 512; i += kEncThreads) sh.ac_tab[i] = __ldg(set + (i >> 8) * 512 + 256 + (i & 255));
+    }
+    if (tid < 64) sh.bin[tid] = 0;
+
+    // ---- 1. locate, stage ----
+    unsigned long long img = 0, v = 0;
+    VisitInfo vi{};
+    int w_lo = 1, w_hi = 0, first_ac = 1;
+    unsigned long long where = 0;
+    if (valid) {
+        split_visit(P, g, img, v);
+        vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
+        first_ac = FULL || vi.ss == 0 ? 1 : vi.ss;
+        w_lo = FULL ? 0 : vi.ss >> 3;
+        w_hi = FULL ? 7 : vi.se >> 3;
+        where = (unsigned long long)vi.blk | (unsigned)w_lo | (unsigned)(w_hi << 3); // blocks are 128-byte aligned
+    }
+    if (!FULL && !__syncthreads_or(valid && vi.se > 0)) { // a CTA inside DC scans (progressive): one code per visit
+        if (valid) {
+            const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
+            int size;
+            uint32_t bits;
+            value_code((int)(int16_t)(__ldg(vi.blk) - prev), size, bits);
+            const uint32_t e = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
+            const unsigned len = e >> 27;
+            if (len) *slot_of(b.slots, g) = (e & kCodeBits) << (32 - len);
+            b.nbits[g] = len;
+        }
+        return;
+    }
+    sh.ptr_or_mask[tid] = where;
+    __syncwarp();
+    { // eight asynchronous 16-byte copies per lane, all in flight together
+        const int w = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int bi = warp * 32 + i * 4 + (lane >> 3);
+            const unsigned long long e = sh.ptr_or_mask[bi];
+            const uint4 *src = reinterpret_cast<const uint4 *>(e & ~127ull);
+            if (src != nullptr && (FULL || (w >= (int)(e & 7) && w <= (int)((e >> 3) & 7)))) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sh.coef + bi * kStageStride + w * 8);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + w) : "memory");
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncwarp();
+
+    // ---- 2. mask of non-zeros in [first_ac, se], DC code, sort key ----
+    unsigned m_lo = 0, m_hi = 0;
+    uint32_t first = 0;
+    if (valid) {
+        const uint4 *mine = reinterpret_cast<const uint4 *>(sh.coef + tid * kStageStride);
+        if (FULL || vi.se > 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                if (!FULL && (w < w_lo || w > w_hi)) continue;
+                const uint4 q = mine[w];
+                // per 16-bit half min(x, 1) = (x != 0); dp2a weighs the two halves 1 and 2 and accumulates
+                unsigned byte = __dp2a_lo(nonzero16x2(q.x), 0x0201u, 0u);
+                byte = __dp2a_lo(nonzero16x2(q.y), 0x0804u, byte);
+                byte = __dp2a_lo(nonzero16x2(q.z), 0x2010u, byte);
+                byte = __dp2a_lo(nonzero16x2(q.w), 0x8040u, byte);
+                if (w < 4) m_lo |= byte << (8 * w);
+                else m_hi |= byte << (8 * (w - 4));
+            }
+            if (FULL) {
+                m_lo &= ~1u;
+            } else {
+                const unsigned long long band = (~0ull << first_ac) & (~0ull >> (63 - vi.se));
+                m_lo &= (unsigned)band;
+                m_hi &= (unsigned)(band >> 32);
+            }
+        }
+        if (FULL || vi.ss == 0) { // write_dc, writer.rs:342-352
+            const int dc = sh.coef[tid * kStageStride];
+            const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
+            int size;
+            uint32_t bits;
+            value_code((int)(int16_t)(dc - prev), size, bits);
+            first = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
+        }
+    }
+    const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
+    __syncthreads();
+    const unsigned rank = atomicAdd(&sh.bin[nnz], 1u);
+    sh.ptr_or_mask[tid] = ((unsigned long long)m_hi << 32) | m_lo;
+    sh.first[tid] = first;
+    sh.info[tid] = (unsigned)vi.se | ((unsigned)first_ac << 8) | ((unsigned)vi.tbl << 16) | (valid ? 1u << 24 : 0u);
+    __syncthreads();
+    if (warp == 0) { // exclusive prefix over the 64 bins, two per lane
+        const unsigned a = sh.bin[2 * lane], c = sh.bin[2 * lane + 1];
+        unsigned inc = a + c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        sh.bin[2 * lane] = inc - a - c;
+        sh.bin[2 * lane + 1] = inc - c;
+    }
+    __syncthreads();
+    sh.order[sh.bin[nnz] + rank] = (uint16_t)tid;
+    __syncthreads();
+
+    // ---- 3. code the visit of rank tid ----
+    const int src = sh.order[tid];
+    const unsigned info = sh.info[src];
+    if (!(info >> 24)) return;
+    const unsigned long long mask = sh.ptr_or_mask[src];
+    const uint32_t dc_code = sh.first[src];
+    const int se = FULL ? 63 : info & 0xFF, fa = FULL ? 1 : (info >> 8) & 0xFF, tbl = (info >> 16) & 0xFF;
+    BitSink sink(b.slots, cta_base + src);
+    sink.put(dc_code & kCodeBits, (int)(dc_code >> 27));
+    if (se > 0) {
+        const int16_t *c = sh.coef + src * kStageStride;
+        if (shared_tables) {
+            code_nonzeros((unsigned)mask, (unsigned)(mask >> 32), fa, se, c, sh.ac_tab + tbl * 256, sink);
+        } else {
+            unsigned long long simg, sv;
+            split_visit(P, cta_base + src, simg, sv);
+            code_nonzeros((unsigned)mask, (unsigned)(mask >> 32), fa, se, c, huff_for(b, simg, tbl, 1), sink);
+        }
+    }
+    b.nbits[cta_base + src] = sink.finish();
 }
 
 // lead of local segment `s`: what the reference writes between the previous segment's last byte
@@ -361,8 +515,9 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     unsigned unit, slot_in_unit;
     split_unit(S, v, unit, slot_in_unit);
     const unsigned R = (unsigned)P.restart;
-    const unsigned seg_in_scan = R ? unit / R : 0;
-    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && unit - seg_in_scan * R == R - 1));
+    unsigned seg_in_scan = 0, seg_r = unit;
+    if (R) divmod(unit, P.div_restart, seg_in_scan, seg_r);
+    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
     if (nb == 0 && !last_of_seg) return;
     const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
     const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
@@ -373,7 +528,7 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     uint32_t *dst = reinterpret_cast<uint32_t *>(b.ustream) + (bitpos >> 5);
     const unsigned sh = (unsigned)(bitpos & 31);
     const unsigned n_words = (nb + 31) >> 5;
-    const uint32_t *src = b.slots + g;
+    const uint32_t *src = slot_of(b.slots, g);
     unsigned pad = 0;
     if (last_of_seg) {
         const unsigned end_bits = (unsigned)((rel_bits + nb) & 7);
@@ -382,7 +537,7 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     uint32_t carry = 0; // bits still to be written into the current destination word (left-aligned)
     bool first = true;
     for (unsigned j = 0; j < n_words; ++j) {
-        uint32_t w = src[(unsigned long long)j * n_visits];
+        uint32_t w = src[j * kSlotTile];
         const unsigned have = (j + 1 == n_words) ? nb - 32 * j : 32u; // valid bits in w (left-aligned)
         if (j + 1 == n_words && pad) { // append the pad ones behind the last code bits when they fit in this word
             if (have + pad <= 32) {
@@ -649,7 +804,10 @@ cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hp, const int16
 
 cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long nv = hp.visits_per_image * n;
-    encode_visits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+    // progressive plans end with an AC band; in every other mode all scans cover the whole block
+    const bool full = hp.scans[hp.n_scans - 1].ss == 0 && hp.scans[hp.n_scans - 1].se == 63;
+    if (full) encode_visits_kernel<true><<<grid_for(nv, kEncThreads), kEncThreads, 0, s>>>(b, nv);
+    else encode_visits_kernel<false><<<grid_for(nv, kEncThreads), kEncThreads, 0, s>>>(b, nv);
     return cudaGetLastError();
 }
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {

@@ -136,6 +136,20 @@ void put_segment(std::vector<uint8_t> &o, uint8_t marker, const uint8_t *data, s
 } // namespace
 
 // ---- Huffman tables (huffman.rs) -----------------------------------------------------------------
+bool HuffTable::device_words(bool ac, uint32_t out[256]) const {
+    for (int s = 0; s < 256; ++s) {
+        const uint32_t len = lookup[s] >> 16, code = lookup[s] & 0xFFFFu;
+        const uint32_t z = ac ? (uint32_t)(s & 15) : (uint32_t)s;
+        if (!ac && s > 15) {
+            out[s] = 0; // DC categories are 0..15
+            continue;
+        }
+        if (len && (len + z > 31 || ((uint64_t)code << z) >> 27)) return false;
+        out[s] = ((len + z) << 27) | (code << z);
+    }
+    return true;
+}
+
 void HuffTable::set(const uint8_t len[16], const uint8_t *vals, size_t n) {
     std::memcpy(length, len, 16);
     values.assign(vals, vals + n);
@@ -437,6 +451,10 @@ void Plan::fill_device_plan(DevPlan &d) const {
     d.blocks_per_image = blocks_per_image;
     d.segs_per_image = segs_per_image;
     d.has_eoi = !is_strip || strip.strip_index + 1 == strip.n_strips;
+    d.div_mcu_cols = make_fastdiv(mcu_cols);
+    d.div_restart = make_fastdiv(p.restart_interval);
+    d.div_vpi = make_fastdiv(visits_per_image >> 32 ? 0u : (unsigned)visits_per_image);
+    if (visits_per_image >> 32) d.div_vpi.d = 0;
     int n = 0;
     for (int c = 0; c < ncomp; ++c) {
         d.comp_h[c] = comps[c].h;
@@ -444,6 +462,7 @@ void Plan::fill_device_plan(DevPlan &d) const {
         d.comp_tbl[c] = comps[c].dc_table;
         d.comp_pw[c] = pad_w[c];
         d.comp_tw[c] = true_w[c];
+        d.div_tw[c] = make_fastdiv(true_w[c]);
         d.comp_off[c] = block_off[c];
         for (int v = 0; v < comps[c].v; ++v)   // MCU order: component, then v outer, h inner (encoder.rs:759-761)
             for (int h = 0; h < comps[c].h; ++h) {
@@ -463,6 +482,7 @@ void Plan::fill_device_plan(DevPlan &d) const {
         ds.se = s.se;
         ds.n_units = s.n_units;
         ds.bpu = s.blocks_per_unit;
+        ds.div_bpu = make_fastdiv(s.blocks_per_unit);
         ds.visit_base = s.visit_base;
         ds.seg_base = s.seg_base;
         ds.n_segs = s.n_segs;

@@ -33,6 +33,11 @@ struct HuffTable {
     void set(const uint8_t len[16], const uint8_t *vals, size_t n);
     // HuffmanTable::new_optimized (Annex K.2), src/huffman.rs:99-221. false if a code would exceed 32 bits.
     bool set_optimized(const uint32_t freq[257]);
+    // What the entropy kernel reads: for symbol s with value size z (s itself for a DC table, s & 15 for an AC
+    // table) the word (code_length + z) << 27 | code << z, i.e. everything of huffman_encode_value's write_bits
+    // argument (src/writer.rs:320-329) except the value bits. false if a coded symbol does not fit
+    // (code_length + z > 31 or code << z beyond 27 bits: impossible for 8-bit samples, where z <= 11).
+    bool device_words(bool ac, uint32_t out[256]) const;
 };
 
 enum class Mode { Interleaved, Sequential, Progressive };

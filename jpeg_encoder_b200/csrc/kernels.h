@@ -22,7 +22,7 @@ struct EntropyBuffers {
     const uint32_t *huff;          // n_huff * kHuffWordsPerImage; n_huff is 1 (shared) or n (optimized)
     int huff_per_image;            // 0: all images share tables[0]; 1: one set per image
     uint32_t *nbits;               // n * visits_per_image
-    uint32_t *slots;               // kSlotWords * n * visits_per_image: word j of visit g at [j * n_visits + g]
+    uint32_t *slots;               // kSlotWords words per visit, tiled by kSlotTile visits (entropy.cu: slot_of)
     unsigned long long *bitpos;    // n * visits_per_image + 1   (exclusive scan of nbits)
     uint32_t *seglen;              // n * segs_per_image          (lead + data + tail bytes of a segment)
     unsigned long long *segpos;    // n * segs_per_image + 1      (exclusive scan of seglen)
@@ -45,6 +45,7 @@ struct EntropyBuffers {
 
 // A visit codes at most 1 + 63 symbols of <= 16 code + 11 value bits = 1728 bits = 54 words.
 constexpr int kSlotWords = 56;
+constexpr int kSlotTile = 256;  // visits per slot tile = threads of the coding CTA
 constexpr int kStuffChunk = 4096; // bytes of unstuffed stream per CTA in the stuffing kernels
 
 // entropy.cu
