@@ -1,0 +1,170 @@
+"""File-level check with an *independent* decoder (tests/t81_decoder.py, written from the T.81 text).
+
+The reference holds no golden JPEGs, so the file bytes of the oracle cannot be compared with the crate's.
+What can be pinned exactly: a conformant entropy decoder must recover from the file precisely the
+quantized coefficients that the unit-pinned functions (colour KATs src/image_buffer.rs:326-421, fDCT
+KATs src/fdct.rs:249-274, quantizer tests src/quantization.rs:314-338) produce, on precisely the block
+grids of src/encoder.rs:713-717 / 1012-1053, with the tables the header announces. That leaves no
+tolerance (the reference's own round-trip tests accept |diff| < 20, src/lib.rs:176-185).
+The GPU variant runs the same check on the product's bytes.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+import images
+import t81_decoder as t81
+from cases import CT, BPP
+
+ZIGZAG = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+          28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54,
+          47, 55, 62, 63]  # T.81 Figure A.6
+
+NCOMP = {"luma": 1, "rgb": 3, "rgba": 3, "bgr": 3, "bgra": 3, "ycbcr": 3, "cmyk": 4, "cmyk_as_ycck": 4, "ycck": 4}
+
+
+def _mode(cfg):
+    """Q13, src/encoder.rs:556-562."""
+    if cfg.get("progressive_scans"):
+        return "progressive"
+    s = cfg.get("sampling") or ((2, 2) if cfg.get("quality", 90) < 90 else (1, 1))
+    if cfg.get("optimize_huffman") or 4 in s:
+        return "sequential"
+    return "interleaved"
+
+
+def check_file(jpg, img, w, h, color, cfg):
+    d = t81.decode(jpg)
+    ncomp = NCOMP[color]
+    mode = _mode(cfg)
+    assert (d.width, d.height, d.precision) == (w, h, 8)
+    assert len(d.components) == ncomp
+    assert [c[0] for c in d.components] == list(range(ncomp))  # Q11: ids are 0-based
+    assert d.progressive == (mode == "progressive")
+    assert d.restart_interval == cfg.get("restart_interval", 0)
+    # Q21 segment order
+    seg = [s for s in d.segments if not s.startswith("APP")]
+    n_dht = 4 if ncomp >= 3 else 2
+    want = ["SOI", "SOF2" if d.progressive else "SOF0", "DQT", "DQT"] + ["DHT"] * n_dht
+    if d.restart_interval:
+        want.append("DRI")
+    assert seg[:len(want)] == want
+    assert seg[len(want):] == ["SOS"] * len(d.scans) + ["EOI"]
+    assert d.segments[1] == "APP0"
+    # scan script
+    if mode == "interleaved":
+        assert len(d.scans) == 1 and d.scans[0]["components"] == list(range(ncomp))
+    elif mode == "sequential":
+        assert [s["components"] for s in d.scans] == [[c] for c in range(ncomp)]
+    else:
+        n = cfg["progressive_scans"]
+        vps = 64 // (n - 1)
+        bands = [(max(i * vps, 1), 63 if i == n - 2 else (i + 1) * vps - 1) for i in range(n - 1)]
+        want_scans = [([c], 0, 0) for c in range(ncomp)] + [([c], lo, hi) for lo, hi in bands for c in range(ncomp)]
+        assert [(s["components"], s["ss"], s["se"]) for s in d.scans] == want_scans
+    # DQT as written: (table >> 3) as u8 in zig-zag order (Q10); both tables always present
+    qsel = cfg.get("qtables", (0, 0))
+    for t in (0, 1):
+        kind = qsel[t]
+        tab, _, _ = orc.quant_table(kind if isinstance(kind, int) else 9, cfg.get("quality", 90), t == 0,
+                                    custom=None if isinstance(kind, int) else list(kind))
+        assert d.qt[t] == (0, [(tab[ZIGZAG[i]] >> 3) & 0xFF for i in range(64)])
+    # coefficients: exact, on the grid each mode codes
+    ref = orc.coefficients(img, w, h, CT[color][0], **cfg)
+    for c in range(ncomp):
+        _, hs, vs, _ = d.components[c]
+        ph, pw = d.mcu_rows * vs, d.mcu_cols * hs
+        r = ref[c].reshape(ph, pw, 64).astype(np.int32)
+        if mode == "interleaved":
+            th, tw = ph, pw
+        else:  # Q14: ceil(ceil(w/8)/h_scale) -- must coincide with the standard's A.2.3 grid the decoder walks
+            tw = -(-(-(-w // 8)) // (d.hmax // hs))
+            th = -(-(-(-h // 8)) // (d.vmax // vs))
+        seen = d.seen[c]
+        assert (seen[:th, :tw] == 1).all(), "every coefficient of the coded grid is coded exactly once"
+        assert (seen[th:] == 0).all() and (seen[:, tw:] == 0).all()
+        np.testing.assert_array_equal(d.coef[c][:th, :tw], r[:th, :tw])
+    return d
+
+
+CASES = [
+    ("rgb", 75, 53, dict(quality=85, sampling=(2, 2))),
+    ("rgb", 64, 48, dict(quality=90, sampling=(1, 1))),
+    ("rgb", 131, 47, dict(quality=95, sampling=(2, 1), restart_interval=3)),
+    ("rgb", 47, 131, dict(quality=70, sampling=(1, 2), optimize_huffman=True)),
+    ("rgb", 100, 60, dict(quality=85, sampling=(2, 2), optimize_huffman=True, restart_interval=7)),
+    ("rgb", 90, 70, dict(quality=80, sampling=(4, 1))),
+    ("rgb", 61, 93, dict(quality=80, sampling=(2, 4), restart_interval=5)),
+    ("rgb", 75, 53, dict(quality=85, sampling=(2, 2), progressive_scans=4)),
+    ("rgb", 75, 53, dict(quality=60, sampling=(2, 2), progressive_scans=2, restart_interval=4)),
+    ("rgb", 40, 40, dict(quality=90, sampling=(1, 1), progressive_scans=64)),
+    ("rgb", 83, 59, dict(quality=85, sampling=(4, 2), progressive_scans=9, optimize_huffman=True)),
+    ("luma", 77, 41, dict(quality=95)),
+    ("luma", 77, 41, dict(quality=50, progressive_scans=5, restart_interval=2)),
+    ("rgba", 50, 34, dict(quality=80)),
+    ("bgr", 50, 34, dict(quality=80, sampling=(2, 1))),
+    ("bgra", 33, 50, dict(quality=80, optimize_huffman=True)),
+    ("ycbcr", 66, 35, dict(quality=88, sampling=(2, 2))),
+    ("cmyk", 52, 37, dict(quality=85, sampling=(1, 1))),
+    ("cmyk", 52, 37, dict(quality=85, sampling=(2, 2), restart_interval=2)),
+    ("cmyk_as_ycck", 52, 37, dict(quality=95, sampling=(1, 1), qtables=(3, 4))),
+    ("ycck", 52, 37, dict(quality=75, sampling=(2, 2), progressive_scans=3)),
+    ("rgb", 64, 64, dict(quality=40, sampling=(2, 2), qtables=(list(range(1, 65)), [3] * 64))),
+    ("rgb", 1, 1, dict(quality=90, sampling=(2, 2))),
+    ("rgb", 8, 9, dict(quality=90, sampling=(2, 2), optimize_huffman=True)),
+]
+IDS = ["%s-%dx%d-%s" % (c, w, h, "-".join("%s%s" % (k[:4], v if not isinstance(v, (list, tuple)) or len(v) < 3 else "c")
+                                          for k, v in sorted(cfg.items()))) for c, w, h, cfg in CASES]
+
+
+def _image(color, w, h, seed):
+    return images.photo_like(w, h, BPP[color], seed=seed)
+
+
+@pytest.mark.parametrize("color,w,h,cfg", CASES, ids=IDS)
+def test_oracle_file_decodes_to_the_unit_pinned_coefficients(color, w, h, cfg):
+    img = _image(color, w, h, seed=11)
+    jpg = orc.encode(img, w, h, CT[color][0], **cfg)
+    check_file(jpg, img, w, h, color, cfg)
+
+
+def test_oracle_noise_image_all_magnitudes():
+    """Uniform noise at q100 reaches the large coefficient categories (DC 11 / AC 10 bits) and long zero runs."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (48, 56, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:16, 0:56]
+    img[:16] = np.where(((yy >> 3) + (xx >> 3)) & 1, 0, 255).astype(np.uint8)[..., None]  # flat 8x8 blocks: DC = -1024 / +1016
+    img[16:24] = np.where((np.arange(56) & 7) < 4, 0, 255).astype(np.uint8)[None, :, None]  # step edges: |AC1| > 512
+    for cfg in (dict(quality=100, sampling=(1, 1)), dict(quality=100, sampling=(2, 2), progressive_scans=4, restart_interval=1),
+                dict(quality=3, sampling=(2, 2), optimize_huffman=True)):
+        jpg = orc.encode(img, 56, 48, orc.RGB, **cfg)
+        d = check_file(jpg, img, 56, 48, "rgb", cfg)
+        if cfg["quality"] == 100:
+            assert int(np.abs(d.coef[0][..., 0]).max()) == 1024  # DC differences of category 11
+            assert int(np.abs(d.coef[0][..., 1:]).max()) >= 512  # AC category 10
+
+
+def test_decoder_rejects_broken_streams():
+    """The checker itself must not be lenient: flipped padding, wrong RST numbering and truncation are errors."""
+    img = _image("rgb", 48, 32, seed=2)
+    jpg = bytearray(orc.encode(img, 48, 32, orc.RGB, quality=85, sampling=(2, 2), restart_interval=2))
+    t81.decode(jpg)
+    i = jpg.index(b"\xff\xd0")
+    bad = bytearray(jpg)
+    bad[i + 1] = 0xD1
+    with pytest.raises(t81.JpegSyntaxError):
+        t81.decode(bad)
+    with pytest.raises(t81.JpegSyntaxError):
+        t81.decode(jpg[:-2] + b"\x00" + jpg[-2:])
+    with pytest.raises((t81.JpegSyntaxError, IndexError)):
+        t81.decode(jpg[:len(jpg) // 2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("color,w,h,cfg", CASES[::3], ids=IDS[::3])
+def test_gpu_file_decodes_to_the_unit_pinned_coefficients(color, w, h, cfg):
+    from cases import gpu_encode
+    img = _image(color, w, h, seed=12)
+    jpg = gpu_encode(img, w, h, color, cfg)
+    check_file(jpg, img, w, h, color, cfg)
