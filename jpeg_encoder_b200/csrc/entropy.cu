@@ -147,7 +147,9 @@ __device__ __forceinline__ void value_code(int v, int &size, uint32_t &bits) {
     int top; // index of the highest set bit, -1 for 0
     asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(a));
     size = top + 1;
-    bits = (uint32_t)(v + (v >> 31)) & ~(~0u << size);
+    uint32_t mask;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(mask) : "r"(size));
+    bits = (uint32_t)(v + (v >> 31)) & mask;
 }
 
 __device__ __forceinline__ unsigned nonzero16x2(unsigned x) {
@@ -169,23 +171,22 @@ __device__ __forceinline__ uint32_t *slot_of(uint32_t *slots, unsigned long long
 struct BitSink {
     unsigned long long acc = 0;
     int n = 0;
-    unsigned words = 0;
-    uint32_t *slot;
+    unsigned off = 0; // bytes written so far, scaled by the tile stride
+    uint32_t *slot0;
 
-    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long g) : slot(slot_of(slots, g)) {}
+    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long g) : slot0(slot_of(slots, g)) {}
     __device__ __forceinline__ void put(uint32_t code, int len) { // len <= 31, n < 32 on entry
         acc = (acc << len) | code;
         n += len;
         if (n >= 32) {
-            *slot = (uint32_t)(acc >> (n - 32));
-            slot += kSlotTile;
             n -= 32;
-            ++words;
+            *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(slot0) + off) = (uint32_t)(acc >> n);
+            off += kSlotTile * 4;
         }
     }
     __device__ __forceinline__ unsigned finish() {
-        if (n > 0) *slot = (uint32_t)(acc << (32 - n)); // left-aligned tail
-        return words * 32 + n;
+        if (n > 0) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(slot0) + off) = (uint32_t)(acc << (32 - n)); // left-aligned tail
+        return off / (kSlotTile * 4) * 32 + n;
     }
 };
 
@@ -212,45 +213,59 @@ __device__ __forceinline__ const uint32_t *huff_for(const EntropyBuffers &b, uns
     return b.huff + (b.huff_per_image ? img * kHuffWordsPerImage : 0) + (size_t)(tbl * 2 + cls) * 256;
 }
 
-// write_ac_block restricted to the band (writer.rs:354-388) for one visit whose non-zero positions are
-// the set bits of `lo`/`hi`: one iteration per non-zero coefficient.
-__device__ __forceinline__ void code_nonzeros(unsigned lo, unsigned hi, int first_ac, int se, const int16_t *__restrict__ c,
-                                              const uint32_t *__restrict__ tab, BitSink &sink) {
-    int next = first_ac; // first position of the current zero run
-    int base = -1, k = 0, cv = 0;
-    // the position and value of the following non-zero are fetched while the current one is coded
-    auto advance = [&]() -> bool {
-        if (lo == 0) {
-            lo = hi;
-            hi = 0;
-            base = 31;
-        }
-        if (lo == 0) return false;
-        k = base + __ffs((int)lo);
-        lo &= lo - 1;
-        cv = c[k];
-        return true;
-    };
-    bool more = advance();
-    while (more) {
-        const int kc = k, cc = cv;
-        more = advance();
-        int run = kc - next;
-        next = kc + 1;
-        if (run > 15) {
-            const uint32_t zrl = tab[0xF0];
+// Zero runs longer than 15 in front of a non-zero coefficient take one ZRL symbol per 16 zeros (writer.rs:369-373).
+// `m` has bit k set for every non-zero coefficient k of the band [first_ac, se]. Returns the positions of the
+// zeros that end such a group of 16: start of the run + 15, + 31, + 47.
+__device__ __forceinline__ unsigned long long zrl_markers(unsigned long long m, int first_ac) {
+    const unsigned long long z = m | (1ull << (first_ac - 1)); // the position in front of the band ends "run 0"
+    unsigned long long s = z; // bit j: z has a set bit in [j - 15, j]
+    s |= s << 1;
+    s |= s << 2;
+    s |= s << 4;
+    s |= s << 8;
+    unsigned long long need = m & ~(s << 1); // non-zeros with 16 or more zeros in front of them
+    unsigned long long marks = 0;
+    while (need) { // rare
+        const int k = __ffsll((long long)need) - 1;
+        need &= need - 1;
+        const int j = 63 - __clzll((long long)(z & ((1ull << k) - 1ull))); // the set bit in front of k
+        for (int t = j + 16; t < k; t += 16) marks |= 1ull << t;
+    }
+    return marks;
+}
+
+// write_ac_block restricted to the band (writer.rs:354-388) for one visit. The positions to code come as two
+// bit-reversed masks: coefficient k of the half [BASE, BASE + 32) is bit 31 - (k - BASE), so the next one in
+// zig-zag order is the highest set bit (one FLO, no bit reversal). One iteration per set bit: a non-zero
+// coefficient, or a ZRL marker (zrl_markers): a zero 15 positions after the start of its run, for which the same
+// arithmetic yields the symbol 0xF0 with no value bits (writer.rs:369-373), so the loop has no ZRL branch.
+template <int BASE>
+__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint32_t *__restrict__ tab, BitSink &sink) {
 #pragma unroll 1
-            do {
-                sink.put(zrl & kCodeBits, (int)(zrl >> 27));
-                run -= 16;
-            } while (run > 15);
-        }
+    while (m) {
+        int p;
+        asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(m));
+        unsigned bit;
+        asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(bit) : "r"(p));
+        m ^= bit;
+        const int k = BASE + 31 - p;
+        int v;
+        asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(c_shared + 2 * k));
+        const int run = k - next; // next = first position of the current zero run; <= 15 thanks to the ZRL markers
+        next = k + 1;
         int size;
         uint32_t bits;
-        value_code(cc, size, bits);
-        const uint32_t e = tab[(run << 4) | size];
+        value_code(v, size, bits);
+        const uint32_t e = (tab + run * 16)[size];
         sink.put((e & kCodeBits) | bits, (int)(e >> 27));
     }
+}
+__device__ __forceinline__ void code_nonzeros(unsigned lo_rev, unsigned hi_rev, int first_ac, int se, const int16_t *__restrict__ c,
+                                              const uint32_t *__restrict__ tab, BitSink &sink) {
+    int next = first_ac;
+    const unsigned c_shared = (unsigned)__cvta_generic_to_shared(c);
+    code_half<0>(lo_rev, next, c_shared, tab, sink);
+    code_half<32>(hi_rev, next, c_shared, tab, sink);
     if (next <= se) { // the band ends in zeros: EOB (writer.rs:383-385)
         const uint32_t e = tab[0];
         sink.put(e & kCodeBits, (int)(e >> 27));
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
     __syncwarp();
 
     // ---- 2. mask of non-zeros in [first_ac, se], DC code, sort key ----
-    unsigned m_lo = 0, m_hi = 0;
+    unsigned m_lo = 0, m_hi = 0; // bit-reversed: coefficient k is bit 31 - k % 32
     uint32_t first = 0;
     if (valid) {
         const uint4 *mine = reinterpret_cast<const uint4 *>(sh.coef + tid * kStageStride);
@@ -351,13 +366,11 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
                 if (w < 4) m_lo |= byte << (8 * w);
                 else m_hi |= byte << (8 * (w - 4));
             }
-            if (FULL) {
-                m_lo &= ~1u;
-            } else {
-                const unsigned long long band = (~0ull << first_ac) & (~0ull >> (63 - vi.se));
-                m_lo &= (unsigned)band;
-                m_hi &= (unsigned)(band >> 32);
-            }
+            unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+            m &= FULL ? ~1ull : (~0ull << first_ac) & (~0ull >> (63 - vi.se));
+            m |= zrl_markers(m, first_ac);
+            m_lo = __brev((unsigned)m); // coded from the highest bit down
+            m_hi = __brev((unsigned)(m >> 32));
         }
         if (FULL || vi.ss == 0) { // write_dc, writer.rs:342-352
             const int dc = sh.coef[tid * kStageStride];
