@@ -42,6 +42,9 @@ WORKLOADS = {
     "c5": (16384, 16384, "rgb", dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048), 1,
            "1 x 16384x16384 RGB progressive (4 scans per component, spectral selection) 4:2:0, restart 2048, "
            "split by restart-aligned strips across the GPUs, pieces gathered to rank 0 (BASELINE config 5)"),
+    "c5o": (16384, 16384, "rgb", dict(quality=85, sampling=(2, 2), optimize_huffman=True, restart_interval=2048), 1,
+            "1 x 16384x16384 RGB 4:2:0 optimized Huffman tables, restart 2048, split by restart-aligned strips: symbol "
+            "histograms all-reduced over NCCL, pieces gathered to rank 0 (SURVEY 8e, optimized variant of config 5)"),
 }
 BPP = {"luma": 1, "rgb": 3, "cmyk_as_ycck": 4}
 DISTINCT = 16  # distinct synthetic frames; the batch repeats them (inputs stay >> L2: 6.2 MB per frame)
@@ -177,7 +180,7 @@ def run_product(args):
 
     width, height, color, cfg, def_batch, desc = WORKLOADS[args.workload]
     cfg = resolve_cfg(cfg)
-    if args.workload == "c5":
+    if args.workload in ("c5", "c5o"):
         return run_strips(args, rank, world, local, dev_t)
     batch = args.batch or def_batch
     bpp = BPP[color]
@@ -378,9 +381,19 @@ def run_strips(args, rank, world, local, dev_t):
     d_strip = images.synth_frame_torch(width, height, bpp, seed=seed, row0=r0, rows=rows, device=dev_t).reshape(-1)
     torch.cuda.synchronize()
 
+    optimized = bool(cfg.get("optimize_huffman"))
+
+    def encode_strip(d_ptr):
+        hist_total = None
+        if optimized:  # tables describe the whole image: all-reduce the strips' symbol histograms first
+            hist, edge = enc.strip_histogram_device(d_ptr, rank, world, r0, rows, width, height, ct)
+            if world > 1:
+                hist, edge = sharding.exchange_strip_histograms(hist, edge, dev_t)
+            hist_total = enc.merge_strip_histograms(hist, edge, width, height, ct)
+        return enc.encode_strip_device(d_ptr, rank, world, r0, rows, width, height, ct, hist_total=hist_total)
+
     def encode_once():
-        d_bytes, offs = enc.encode_strip_device(d_strip.data_ptr(), rank, world, r0, rows, width, height, ct)
-        return d_bytes, offs
+        return encode_strip(d_strip.data_ptr())
 
     def step(gather=True):
         d_bytes, offs = encode_once()
@@ -454,7 +467,7 @@ def run_strips(args, rank, world, local, dev_t):
     d2h = 0
     for _ in range(e2e_steps):
         d_stage.copy_(h_strip, non_blocking=True)
-        d_bytes, offs = enc.encode_strip_device(d_stage.data_ptr(), rank, world, r0, rows, width, height, ct)
+        d_bytes, offs = encode_strip(d_stage.data_ptr())
         if world > 1:
             o = sharding.gather_strip_pieces(_as_tensor(d_bytes, offs[-1], dev_t), offs, rank, world, dev_t)
         else:
@@ -486,7 +499,8 @@ def run_strips(args, rank, world, local, dev_t):
         "config": {"workload": desc, "workload_id": args.workload, "width": width, "height": height,
                    "strips": [[int(a), int(b)] for a, b in strips], "settings": cfg, "bytes_out": out_bytes,
                    "l2": "strip input %.0f MB per GPU, larger than L2" % (width * rows * bpp / 1e6),
-                   "collective": "one all_gather of piece sizes + one NCCL send per non-zero rank (gather to rank 0)"},
+                   "collective": ("all-reduce of the 4 x 257 symbol histogram + all_gather of edge DCs, then " if optimized else "")
+                   + "one all_gather of piece sizes + one NCCL send per non-zero rank (gather to rank 0)"},
         "clocks": clocks,
         "e2e": {"value": mp * e2e_steps / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": width * height * bpp,
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,

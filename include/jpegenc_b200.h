@@ -153,10 +153,26 @@ int jpgb_plan_strips(const jpgb_params *p, uint32_t max_strips, jpgb_strip *stri
 /* Encode one strip. `p->height` is the whole image's height; `d_pixels` (device) points at the
  * strip's first row. On return *d_bytes is device memory owned by the context holding the strip's
  * pieces back to back and piece_offsets[0..n_scans] (host) delimits piece k as
- * [piece_offsets[k], piece_offsets[k+1]). Optimized Huffman tables are not available with strips
- * (they need the whole image's histogram). */
+ * [piece_offsets[k], piece_offsets[k+1]). With optimized Huffman tables use the _optimized entry below. */
 int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
                              const void **d_bytes, uint64_t *piece_offsets);
+
+/* Strips with optimized Huffman tables (src/encoder.rs:1086-1200 builds the tables from the symbol
+ * histogram of the whole image, so the strips exchange theirs first):
+ *  1. every strip: jpgb_strip_histogram_device -> hist[table 0|1][dc|ac][257] of the strip, its DC chain
+ *     started at 0, and edge_dc[0..3] / edge_dc[4..7] = DC of the first / last block of each component;
+ *  2. the caller sums the histograms over the strips (an all-reduce; jpeg_encoder_b200/sharding.py does it
+ *     with NCCL) and gathers the edge_dc arrays in strip order (n_strips * 8 values);
+ *  3. jpgb_merge_strip_histograms re-chains the first DC difference of every strip to the block in front
+ *     of it (the reference's histogram never resets the DC predictor, Q17) -> hist_total;
+ *  4. every strip: jpgb_encode_strip_device_optimized with hist_total. */
+#define JPGB_HIST_WORDS (2 * 2 * 257)
+int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                                uint32_t hist[JPGB_HIST_WORDS], int16_t edge_dc[8]);
+int jpgb_merge_strip_histograms(const jpgb_params *p, uint32_t n_strips, const uint32_t hist_sum[JPGB_HIST_WORDS],
+                                const int16_t *edge_dc /* n_strips * 8 */, uint32_t hist_total[JPGB_HIST_WORDS]);
+int jpgb_encode_strip_device_optimized(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                                       const uint32_t hist_total[JPGB_HIST_WORDS], const void **d_bytes, uint64_t *piece_offsets);
 
 /* Copy `n` bytes of context-owned (or any) device memory to host memory; synchronous on the context's stream. */
 int jpgb_download(jpgb_encoder *enc, const void *d_src, size_t n, void *host_dst);

@@ -150,8 +150,10 @@ int validate_and_plan(jpgb_encoder *enc, const jpgb_params *p, size_t len_each, 
 
 // The whole device pipeline for `n` device-resident images. On success the files lie back to back
 // in enc->out and `offsets` (host, n + 1) delimits them.
+// `given_hist` (strips with optimized tables): the symbol histogram of the *whole* image, [table][dc|ac][257],
+// used instead of the one of these pixels.
 int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, size_t image_stride, uint32_t n,
-                  std::vector<uint64_t> &offsets, std::vector<uint64_t> *piece_offsets = nullptr) {
+                  std::vector<uint64_t> &offsets, std::vector<uint64_t> *piece_offsets = nullptr, const uint32_t *given_hist = nullptr) {
     cudaStream_t st = enc->stream;
     DevPlan hp;
     plan.fill_device_plan(hp);
@@ -189,13 +191,17 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     if (optimized) {
         StageTimer t(enc, 1);
         const size_t hist_words = (size_t)n * 2 * 2 * 257;
-        CK(enc->hist.reserve(hist_words * 4), "alloc histogram");
         CK(enc->h_hist.reserve(hist_words * 4), "alloc histogram (host)");
-        CK(cudaMemsetAsync(enc->hist.p, 0, hist_words * 4, st), "clear histogram");
-        CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
-        enc->launches += n;
-        CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_words * 4, cudaMemcpyDeviceToHost, st), "download histogram");
-        CK(cudaStreamSynchronize(st), "histogram sync");
+        if (given_hist) {
+            std::memcpy(enc->h_hist.p, given_hist, hist_words * 4); // n == 1
+        } else {
+            CK(enc->hist.reserve(hist_words * 4), "alloc histogram");
+            CK(cudaMemsetAsync(enc->hist.p, 0, hist_words * 4, st), "clear histogram");
+            CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
+            enc->launches += n;
+            CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_words * 4, cudaMemcpyDeviceToHost, st), "download histogram");
+            CK(cudaStreamSynchronize(st), "histogram sync");
+        }
         const int max_tables = plan.ncomp < 2 ? plan.ncomp : 2; // encoder.rs:1089
         for (uint32_t i = 0; i < n; ++i)
             for (int tb = 0; tb < max_tables; ++tb)
@@ -651,7 +657,7 @@ int jpgb_plan_strips(const jpgb_params *p, uint32_t max_strips, jpgb_strip *stri
     const int rc = plan.build(*p);
     if (rc != JPGB_OK) return rc;
     const uint32_t R = p->restart_interval;
-    if (R == 0 || p->optimize_huffman) return JPGB_ERR_BAD_PARAMS;
+    if (R == 0) return JPGB_ERR_BAD_PARAMS;
     auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
     // a strip may start at MCU row r only if r * (units per MCU row) is a multiple of R in every scan
     uint64_t step = 1;
@@ -679,11 +685,13 @@ int jpgb_plan_strips(const jpgb_params *p, uint32_t max_strips, jpgb_strip *stri
     return JPGB_OK;
 }
 
-int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
-                             const void **d_bytes, uint64_t *piece_offsets) {
+static int encode_strip(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels, const uint32_t *hist_total,
+                        const void **d_bytes, uint64_t *piece_offsets) {
     if (!enc) return JPGB_ERR_BAD_PARAMS;
     if (!p || !strip || !d_pixels || !d_bytes || !piece_offsets) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
     if (p->color_type > JPGB_YCCK) return fail(enc, JPGB_ERR_BAD_PARAMS, "bad color_type");
+    if ((p->optimize_huffman != 0) != (hist_total != nullptr))
+        return fail(enc, JPGB_ERR_BAD_PARAMS, "optimized tables with strips take the whole image's histogram (jpgb_encode_strip_device_optimized); other settings take none");
     Plan plan;
     const int rc = plan.build(*p, strip);
     if (rc != JPGB_OK) return fail(enc, rc, "settings or strip geometry do not allow strip encoding (needs restart intervals aligned in every scan)");
@@ -691,11 +699,93 @@ int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb
     timing_begin(enc);
     std::vector<uint64_t> off, pieces;
     const size_t stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
-    const int rc2 = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), stride, 1, off, &pieces);
+    const int rc2 = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), stride, 1, off, &pieces, hist_total);
     if (rc2 != JPGB_OK) return rc2;
     timing_end(enc);
     std::memcpy(piece_offsets, pieces.data(), pieces.size() * 8);
     *d_bytes = enc->out.p;
+    return JPGB_OK;
+}
+
+int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                             const void **d_bytes, uint64_t *piece_offsets) {
+    return encode_strip(enc, p, strip, d_pixels, nullptr, d_bytes, piece_offsets);
+}
+
+int jpgb_encode_strip_device_optimized(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                                       const uint32_t hist_total[JPGB_HIST_WORDS], const void **d_bytes, uint64_t *piece_offsets) {
+    if (enc && !hist_total) return fail(enc, JPGB_ERR_BAD_PARAMS, "null histogram");
+    return encode_strip(enc, p, strip, d_pixels, hist_total, d_bytes, piece_offsets);
+}
+
+int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
+                                uint32_t hist[JPGB_HIST_WORDS], int16_t edge_dc[8]) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!p || !strip || !d_pixels || !hist || !edge_dc) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    if (p->color_type > JPGB_YCCK || !p->optimize_huffman) return fail(enc, JPGB_ERR_BAD_PARAMS, "strip histograms belong to optimized Huffman tables");
+    Plan plan;
+    const int rc = plan.build(*p, strip);
+    if (rc != JPGB_OK) return fail(enc, rc, "settings or strip geometry do not allow strip encoding (needs restart intervals aligned in every scan)");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    cudaStream_t st = enc->stream;
+    DevPlan hp;
+    plan.fill_device_plan(hp);
+    StageAParams ap;
+    plan.fill_stage_a(ap);
+    CK(enc->coef.reserve(plan.blocks_per_image * 128), "alloc coefficients");
+    CK(enc->plan.reserve(sizeof(DevPlan)), "alloc plan");
+    if (enc->last_plan.size() != sizeof(DevPlan) || std::memcmp(enc->last_plan.data(), &hp, sizeof(DevPlan)) != 0) {
+        enc->last_plan.assign(reinterpret_cast<const uint8_t *>(&hp), reinterpret_cast<const uint8_t *>(&hp) + sizeof(DevPlan));
+        CK(cudaMemcpyAsync(enc->plan.p, enc->last_plan.data(), sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
+        CK(cudaStreamSynchronize(st), "plan upload sync");
+    }
+    ap.pixels = static_cast<const uint8_t *>(d_pixels);
+    ap.coef = enc->coef.as<int16_t>();
+    ap.image_stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
+    CK(launch_stage_a(ap, 1, st), "stage A launch");
+    const size_t hist_bytes = JPGB_HIST_WORDS * 4;
+    CK(enc->hist.reserve(hist_bytes), "alloc histogram");
+    CK(enc->h_hist.reserve(hist_bytes + 16), "alloc histogram (host)");
+    CK(cudaMemsetAsync(enc->hist.p, 0, hist_bytes, st), "clear histogram");
+    CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), 1, enc->hist.as<uint32_t>(), st), "histogram launch");
+    enc->launches = 2;
+    CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_bytes, cudaMemcpyDeviceToHost, st), "download histogram");
+    // DC of the first and of the last block of every component's true grid (the histogram chains DC differences
+    // across the whole image without restart resets, encoder.rs:1086-1200: the neighbours need them)
+    int16_t *edge = reinterpret_cast<int16_t *>(enc->h_hist.as<uint8_t>() + hist_bytes);
+    std::memset(edge, 0, 16);
+    for (int c = 0; c < plan.ncomp; ++c) {
+        const uint64_t first = plan.block_off[c], last = plan.block_off[c] + (uint64_t)(plan.true_h[c] - 1) * plan.pad_w[c] + plan.true_w[c] - 1;
+        CK(cudaMemcpyAsync(edge + c, enc->coef.as<int16_t>() + first * 64, 2, cudaMemcpyDeviceToHost, st), "read edge DC");
+        CK(cudaMemcpyAsync(edge + 4 + c, enc->coef.as<int16_t>() + last * 64, 2, cudaMemcpyDeviceToHost, st), "read edge DC");
+    }
+    CK(cudaStreamSynchronize(st), "histogram sync");
+    std::memcpy(hist, enc->h_hist.p, hist_bytes);
+    std::memcpy(edge_dc, edge, 16);
+    return JPGB_OK;
+}
+
+int jpgb_merge_strip_histograms(const jpgb_params *p, uint32_t n_strips, const uint32_t hist_sum[JPGB_HIST_WORDS], const int16_t *edge_dc,
+                                uint32_t hist_total[JPGB_HIST_WORDS]) {
+    if (!p || !hist_sum || !edge_dc || !hist_total || n_strips == 0) return JPGB_ERR_BAD_PARAMS;
+    Plan plan;
+    const int rc = plan.build(*p);
+    if (rc != JPGB_OK) return rc;
+    std::memcpy(hist_total, hist_sum, JPGB_HIST_WORDS * 4);
+    auto category = [](int diff) { // get_num_bits of the i16 difference, encoder.rs:1244-1257
+        int a = (int16_t)diff;
+        a = a < 0 ? -a : a;
+        int n = 0;
+        while (a) ++n, a >>= 1;
+        return n;
+    };
+    for (uint32_t s = 1; s < n_strips; ++s)
+        for (int c = 0; c < plan.ncomp; ++c) {
+            uint32_t *dc = hist_total + (size_t)plan.comps[c].dc_table * 2 * 257;
+            const int first = edge_dc[s * 8 + c], prev_last = edge_dc[(s - 1) * 8 + 4 + c];
+            dc[category(first)] -= 1;             // the strip counted its first block against a predictor of 0
+            dc[category(first - prev_last)] += 1; // the whole image chains it to the block before
+        }
     return JPGB_OK;
 }
 

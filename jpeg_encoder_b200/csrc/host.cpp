@@ -364,7 +364,7 @@ int Plan::build(const jpgb_params &params, const jpgb_strip *st) {
         }
     }
     if (is_strip) {
-        if (!p.restart_interval || p.optimize_huffman) return JPGB_ERR_BAD_PARAMS;
+        if (!p.restart_interval) return JPGB_ERR_BAD_PARAMS;
         if (strip.n_strips == 0 || strip.strip_index >= strip.n_strips || strip.rows == 0) return JPGB_ERR_BAD_PARAMS;
         if (strip.first_row % (8 * vmax) != 0 || (uint32_t)strip.first_row + strip.rows > strip.full_height) return JPGB_ERR_BAD_PARAMS;
         if (strip.strip_index + 1 < strip.n_strips && strip.rows % (8 * vmax) != 0) return JPGB_ERR_BAD_PARAMS;

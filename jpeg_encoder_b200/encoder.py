@@ -156,6 +156,7 @@ class _Strip(C.Structure):
 
 
 N_STAGES = 7
+HIST_WORDS = 2 * 2 * 257  # JPGB_HIST_WORDS
 STAGE_NAMES = ("colour_dct_quant", "histogram_tables", "symbol_sizes_scans", "emit_bits", "stuff_scatter", "h2d", "d2h")
 
 _lib = None
@@ -192,6 +193,10 @@ def load_library():
     l.jpgb_scan_count.argtypes = [C.POINTER(_Params), C.POINTER(C.c_uint32)]
     l.jpgb_plan_strips.argtypes = [C.POINTER(_Params), C.c_uint32, C.POINTER(_Strip), C.POINTER(C.c_uint32)]
     l.jpgb_encode_strip_device.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Strip), vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    l.jpgb_encode_strip_device_optimized.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Strip), vp, C.POINTER(C.c_uint32), C.POINTER(vp),
+                                                     C.POINTER(C.c_uint64)]
+    l.jpgb_strip_histogram_device.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Strip), vp, C.POINTER(C.c_uint32), C.POINTER(C.c_int16)]
+    l.jpgb_merge_strip_histograms.argtypes = [C.POINTER(_Params), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int16), C.POINTER(C.c_uint32)]
     l.jpgb_download.argtypes = [vp, vp, C.c_size_t, vp]
     l.jpgb_coef_layout_for.argtypes = [C.POINTER(_Params), C.POINTER(_CoefLayout)]
     l.jpgb_stage_a_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32, vp]
@@ -516,18 +521,48 @@ class Encoder:
             raise EncodingError(rc, "strips need a restart interval that divides every scan's units per MCU-row group")
         return [(arr[i].first_row, arr[i].rows) for i in range(n.value)]
 
-    def encode_strip_device(self, d_pixels, strip_index, n_strips, first_row, rows, width, full_height, color_type):
-        """Encode one strip (device pointer at its first row). Returns (device pointer, piece offsets[n_scans+1])."""
+    def encode_strip_device(self, d_pixels, strip_index, n_strips, first_row, rows, width, full_height, color_type, hist_total=None):
+        """Encode one strip (device pointer at its first row). Returns (device pointer, piece offsets[n_scans+1]).
+        With optimized Huffman tables pass the whole image's histogram (merge_strip_histograms)."""
         dev = self._dev()
         p = self._params(width, full_height, ColorType(color_type))
         st = _Strip(strip_index, n_strips, first_row, rows, full_height)
         n_scans = self.scan_count(width, full_height, color_type)
         d_bytes = C.c_void_p()
         offs = (C.c_uint64 * (n_scans + 1))()
-        rc = dev.lib.jpgb_encode_strip_device(dev.handle, C.byref(p), C.byref(st), C.c_void_p(d_pixels), C.byref(d_bytes), offs)
+        if hist_total is None:
+            rc = dev.lib.jpgb_encode_strip_device(dev.handle, C.byref(p), C.byref(st), C.c_void_p(d_pixels), C.byref(d_bytes), offs)
+        else:
+            h = (C.c_uint32 * HIST_WORDS)(*[int(x) for x in hist_total])
+            rc = dev.lib.jpgb_encode_strip_device_optimized(dev.handle, C.byref(p), C.byref(st), C.c_void_p(d_pixels), h, C.byref(d_bytes), offs)
         if rc != 0:
             self._raise(rc)
         return d_bytes.value, list(offs)
+
+    def strip_histogram_device(self, d_pixels, strip_index, n_strips, first_row, rows, width, full_height, color_type):
+        """Optimized tables with strips, step 1: (hist[HIST_WORDS], edge_dc[8]) of one strip (include/jpegenc_b200.h)."""
+        dev = self._dev()
+        p = self._params(width, full_height, ColorType(color_type))
+        st = _Strip(strip_index, n_strips, first_row, rows, full_height)
+        hist = (C.c_uint32 * HIST_WORDS)()
+        edge = (C.c_int16 * 8)()
+        rc = dev.lib.jpgb_strip_histogram_device(dev.handle, C.byref(p), C.byref(st), C.c_void_p(d_pixels), hist, edge)
+        if rc != 0:
+            self._raise(rc)
+        return list(hist), list(edge)
+
+    def merge_strip_histograms(self, hist_sum, edge_dc, width, full_height, color_type):
+        """Step 3: hist_sum = element-wise sum of the strips' histograms, edge_dc = their edge_dc arrays in strip
+        order (n_strips * 8). Returns the whole image's histogram. Host only."""
+        p = self._params(width, full_height, ColorType(color_type))
+        n = len(edge_dc) // 8
+        hs = (C.c_uint32 * HIST_WORDS)(*[int(x) for x in hist_sum])
+        ed = (C.c_int16 * (n * 8))(*[int(x) for x in edge_dc])
+        out = (C.c_uint32 * HIST_WORDS)()
+        rc = load_library().jpgb_merge_strip_histograms(C.byref(p), n, hs, ed, out)
+        if rc != 0:
+            raise EncodingError(rc)
+        return list(out)
 
     def build_header(self, width, height, color_type):
         """SOI .. first SOS as the host planner writes them (default Huffman tables). No GPU needed."""

@@ -4,7 +4,8 @@
 * One very large image shards by strips of whole MCU rows whose boundaries are restart boundaries
   of every scan. Each rank encodes its strip; the only exchange is the gather of the strips'
   per-scan byte pieces to rank 0 (sizes first, then one grouped batch of variable-length sends over
-  NCCL/NVLink), where they are concatenated scan-major.
+  NCCL/NVLink), where they are concatenated scan-major. With optimized Huffman tables the strips
+  first all-reduce their symbol histograms (the tables describe the whole image).
 
 The exchange functions work on whatever device the tensors live on: NCCL with CUDA tensors on the
 B200 box, gloo with CPU tensors in the world_size-2 CPU tests.
@@ -34,6 +35,19 @@ def assemble_pieces(pieces_by_strip):
 
 def split_pieces(buf, offsets):
     return [bytes(buf[offsets[k]:offsets[k + 1]]) for k in range(len(offsets) - 1)]
+
+
+def exchange_strip_histograms(hist, edge_dc, device, group=None):
+    """Optimized Huffman tables with strips (include/jpegenc_b200.h, steps 2): the strips' symbol histograms
+    are summed with one all-reduce (2 x 2 x 257 u32; NCCL over NVLink on the GPU box) and the DC values at
+    the strip edges are all-gathered in rank order. Returns (hist_sum list, edge_dc list of world * 8)."""
+    h = torch.tensor(hist, dtype=torch.int64, device=device)  # NCCL has no u32 sum; counts fit easily
+    dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+    e = torch.tensor(edge_dc, dtype=torch.int32, device=device)
+    world = dist.get_world_size(group)
+    table = torch.empty(world * 8, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(table, e, group=group)
+    return h.cpu().tolist(), table.cpu().tolist()
 
 
 def gather_strip_pieces(local_bytes, piece_offsets, rank, world, device, group=None):

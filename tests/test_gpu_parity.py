@@ -284,11 +284,19 @@ def _encode_by_strips(img, w, h, color, cfg, max_strips):
     strips = enc.plan_strips(w, h, ct, max_strips)
     dev = je.default_device(0)
     flat = np.ascontiguousarray(img).reshape(h, -1)
+    d_px = [torch.from_numpy(flat[r0:r0 + rows].copy()).cuda() for r0, rows in strips]
+    torch.cuda.synchronize()
+    hist_total = None
+    if cfg.get("optimize_huffman"):  # what sharding.exchange_strip_histograms does across ranks, here in one process
+        hists, edges = [], []
+        for i, (r0, rows) in enumerate(strips):
+            hi, ed = enc.strip_histogram_device(d_px[i].data_ptr(), i, len(strips), r0, rows, w, h, ct)
+            hists.append(hi)
+            edges += ed
+        hist_total = enc.merge_strip_histograms([sum(col) for col in zip(*hists)], edges, w, h, ct)
     pieces = []
     for i, (r0, rows) in enumerate(strips):
-        d_px = torch.from_numpy(flat[r0:r0 + rows].copy()).cuda()
-        torch.cuda.synchronize()
-        d_bytes, offs = enc.encode_strip_device(d_px.data_ptr(), i, len(strips), r0, rows, w, h, ct)
+        d_bytes, offs = enc.encode_strip_device(d_px[i].data_ptr(), i, len(strips), r0, rows, w, h, ct, hist_total=hist_total)
         pieces.append(sharding.split_pieces(dev.download(d_bytes, offs[-1]), offs))
     return sharding.assemble_pieces(pieces), len(strips)
 
@@ -300,6 +308,9 @@ def _encode_by_strips(img, w, h, color, cfg, max_strips):
     ("sequential_4_1", "rgb", 512, 256, dict(quality=75, sampling=(4, 1), restart_interval=16), 4),
     ("luma", "luma", 384, 512, dict(quality=95, restart_interval=48), 8),
     ("ycck_progressive", "cmyk_as_ycck", 256, 256, dict(quality=90, sampling=(1, 1), progressive_scans=3, restart_interval=32), 4),
+    ("optimized_420", "rgb", 512, 400, dict(quality=85, sampling=(2, 2), optimize_huffman=True, restart_interval=64), 4),
+    ("optimized_progressive", "rgb", 384, 384, dict(quality=70, sampling=(2, 1), optimize_huffman=True, progressive_scans=5, restart_interval=48), 8),
+    ("optimized_cmyk", "cmyk", 256, 320, dict(quality=90, sampling=(2, 2), optimize_huffman=True, restart_interval=16), 5),
 ])
 def test_strips_concatenate_to_the_whole_image(name, color, w, h, cfg, max_strips):
     img = _img(color, w, h, seed=21)

@@ -51,8 +51,31 @@ def test_plan_strips_alignment_rules():
     assert len(_enc(65535).plan_strips(640, 480, je.ColorType.Rgb, 8)) == 1
     with pytest.raises(je.EncodingError):
         _enc(0).plan_strips(1920, 1080, je.ColorType.Rgb, 8)  # no restart interval: replicas only
-    with pytest.raises(je.EncodingError):
-        _enc(64, optimize=True).plan_strips(1920, 1080, je.ColorType.Rgb, 8)  # needs a global histogram
+    # optimized tables: sequential scans (one per component); the strips exchange histograms first
+    strips = _enc(64, optimize=True).plan_strips(1920, 1080, je.ColorType.Rgb, 8)
+    assert len(strips) > 1 and sum(n for _, n in strips) == 1080
+
+
+def test_merge_strip_histograms_rechains_the_first_dc():
+    """The reference's histogram chains DC differences over the whole component without restart resets
+    (src/encoder.rs:1086-1200, Q17): a strip counted its first block against 0, the merge re-chains it."""
+    e = _enc(64, optimize=True)
+    W = je.encoder.HIST_WORDS
+    hist = [0] * W
+    # two strips; table 0 <- Y, table 1 <- Cb + Cr. Strip 1: first DCs (Y, Cb, Cr) = (100, -3, 0); strip 0 last DCs = (90, 5, 0)
+    # each strip contributed cat(first - 0): strip 0 firsts are (7, 0, 0) -> cats 3, 0, 0; strip 1 -> cats 7, 2, 0
+    hist[0 * 257 + 3] += 1
+    hist[0 * 257 + 7] += 1
+    hist[2 * 257 + 0] += 3
+    hist[2 * 257 + 2] += 1
+    hist[1 * 257 + 0x11] = 5  # AC bins are left alone
+    edge = [7, 0, 0, 0, 90, 5, 0, 0,   100, -3, 0, 0, 1, 1, 1, 0]
+    out = e.merge_strip_histograms(hist, edge, 1920, 1080, je.ColorType.Rgb)
+    want = list(hist)
+    want[0 * 257 + 7] -= 1; want[0 * 257 + 4] += 1      # Y: 100 - 90 = 10 -> category 4
+    want[2 * 257 + 2] -= 1; want[2 * 257 + 4] += 1      # Cb: -3 - 5 = -8 -> category 4
+    # Cr: 0 - 0 = 0 -> category 0, unchanged
+    assert out == want
 
 
 def test_assemble_is_scan_major():
@@ -75,6 +98,11 @@ def _worker(rank, world, port, q):
     out = sharding.gather_strip_pieces(buf, offs, rank, world, torch.device("cpu"))
     if rank == 0:
         q.put(bytes(out.tolist()))
+    # optimized tables with strips: histogram all-reduce + edge all-gather
+    hist = [rank + 1] * je.encoder.HIST_WORDS
+    hs, edges = sharding.exchange_strip_histograms(hist, [rank * 10 + i for i in range(8)], torch.device("cpu"))
+    assert hs == [sum(r + 1 for r in range(world))] * je.encoder.HIST_WORDS
+    assert edges == [r * 10 + i for r in range(world) for i in range(8)]
     lo, hi = sharding.shard_batch(11, world, rank)
     t = torch.tensor([hi - lo])
     dist.all_reduce(t)
