@@ -293,6 +293,24 @@ def run_product(args):
         e2e_s = float(t.item())
     e2e_value = mp_per_step * world * e2e_steps / e2e_s
 
+    # what the link alone can do: the same pinned frames copied to the device back to back, nothing else running
+    # (explains the end-to-end number: it moves bpp bytes per pixel over PCIe)
+    stage_d = torch.empty(min(batch, 64) * img_bytes, dtype=torch.uint8, device=dev_t)
+    n_copy = min(batch, 256)
+
+    def copy_all():
+        for i in range(n_copy):
+            k = i % min(batch, 64)
+            stage_d[k * img_bytes:(k + 1) * img_bytes].copy_(pinned[order[i]], non_blocking=True)
+
+    copy_all()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    copy_all()
+    torch.cuda.synchronize()
+    h2d_gbs = n_copy * img_bytes / (time.perf_counter() - t0) / 1e9
+    del stage_d
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,7 +363,10 @@ def run_product(args):
                    if batch * img_bytes > 200e6 else "inputs smaller than L2 (%.1f MB): single-image latency case" % (batch * img_bytes / 1e6)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": batch * img_bytes * world,
-                "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "api": "jpgb_encode_batch_pinned (pinned host pixels -> host JPEG files; chunked upload/encode/download overlap)"},
+                "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "api": "jpgb_encode_batch_pinned (pinned host pixels -> host JPEG files; chunked upload/encode/download overlap)",
+                "h2d_link_gbs_measured": h2d_gbs, "h2d_gbs_in_e2e": batch * img_bytes * e2e_steps / e2e_s / 1e9,
+                "frac_of_link": (batch * img_bytes * e2e_steps / e2e_s / 1e9) / h2d_gbs,
+                "note": "end to end is bound by the host->device link (bpp bytes per pixel over PCIe): frac_of_link = h2d_gbs_in_e2e / h2d_link_gbs_measured (rank 0)"},
         "gpu_launches": launches,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "roofline": roofline,
