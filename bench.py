@@ -84,6 +84,12 @@ def cpu_encode_rate(frames, width, height, color, cfg, seconds, threads):
     from oracle import oracle as orc
     orc.lib(native=True)  # built with -march=native on the machine that times it
     ct = CT[color][0]
+    if orc.has_simd(native=True):  # AVX2 colour + fDCT where the reference's `simd` feature has its own; same bytes, checked here
+        orc.set_simd(False, native=True)
+        plain = orc.encode(frames[0], width, height, ct, native=True, **cfg)
+        orc.set_simd(True, native=True)
+        if orc.encode(frames[0], width, height, ct, native=True, **cfg) != plain:
+            raise SystemExit("bench.py: the oracle's AVX2 path differs from its scalar path")
     done = [0] * threads
     stop = time.perf_counter() + seconds
 
@@ -349,7 +355,8 @@ def run_product(args):
                "sample": "%d encodes of the workload's frames, one encode per thread on %d threads (%.0f s); single thread: %d encodes"
                          % (nN, cores, args.cpu_seconds, n1),
                "single_thread_value": v1,
-               "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native; the Rust crate cannot be built in this image"}
+               "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native, AVX2 colour conversion and fDCT like the crate's simd feature "
+                       "(quantizer and entropy coder scalar, as in the crate); the Rust crate cannot be built in this image"}
 
     line = {
         "metric": "megapixels/sec encoded, byte-identical to the reference restatement",
@@ -582,7 +589,8 @@ def run_reference(args):
         "config": {"workload": desc, "workload_id": args.workload, "width": width, "height": height,
                    "settings": {k: (v if k != "qtables" else "custom u16[64] x2") for k, v in cfg.items()}},
         "cpu_baseline": {"value": value, "unit": "megapixels/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native; no Rust toolchain in the image"},
+                         "note": "C restatement of jpeg-encoder 0.7.0 (oracle/), gcc -O3 -march=native, AVX2 colour conversion and fDCT like the crate's simd feature "
+                                 "(quantizer and entropy coder scalar, as in the crate); no Rust toolchain in the image"},
         "e2e": {"value": value, "unit": "megapixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

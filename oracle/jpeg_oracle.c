@@ -9,6 +9,21 @@
 
 #include <stdlib.h>
 #include <string.h>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
+
+/* CPU-baseline switch: 1 = use the AVX2 colour conversion and fDCT below where the reference's `simd`
+ * feature uses its own (src/avx2/ycbcr.rs, src/avx2/fdct.rs). Same bits either way (tests compare). */
+static int g_simd = 0;
+void orc_set_simd(int on) { g_simd = on; }
+int orc_has_simd(void) {
+#if defined(__AVX2__)
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------
  * byte sink (the reference writes into a user `W: JfifWrite`; here: a growing buffer)
@@ -127,6 +142,40 @@ static int num_components(uint8_t ct) { /* src/encoder.rs:55-65 + adaptors' get_
     }
 }
 
+#if defined(__AVX2__)
+/* Eight RGB(A) pixels per step (role of src/avx2/ycbcr.rs:58-125, which the `simd` feature selects for
+ * the Rgb / Rgba adaptors): one gather fetches the three channel bytes of each pixel, then the same
+ * i32 multiply / add / shift as orc_rgb_to_ycbcr. Returns how many pixels of the row it converted
+ * (the last ones are left to the scalar loop so the 4-byte gathers never read past the row). */
+static size_t rgb_row_avx2(const uint8_t *line, size_t width, int bpp, uint8_t *y, uint8_t *cb, uint8_t *cr) {
+    const __m256i idx = _mm256_mullo_epi32(_mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7), _mm256_set1_epi32(bpp));
+    const __m256i ff = _mm256_set1_epi32(0xFF), half = _mm256_set1_epi32(0x7FFF), bias = _mm256_set1_epi32((128 << 16) + 0x7FFF);
+    size_t x = 0;
+    for (; x + 9 <= width; x += 8) {
+        const __m256i px = _mm256_i32gather_epi32((const int *)(line + x * bpp), idx, 1);
+        const __m256i r = _mm256_and_si256(px, ff), g = _mm256_and_si256(_mm256_srli_epi32(px, 8), ff),
+                      b = _mm256_and_si256(_mm256_srli_epi32(px, 16), ff);
+        __m256i vy = _mm256_add_epi32(_mm256_add_epi32(_mm256_mullo_epi32(r, _mm256_set1_epi32(19595)), _mm256_mullo_epi32(g, _mm256_set1_epi32(38470))),
+                                      _mm256_add_epi32(_mm256_mullo_epi32(b, _mm256_set1_epi32(7471)), half));
+        __m256i vcb = _mm256_add_epi32(_mm256_add_epi32(_mm256_mullo_epi32(r, _mm256_set1_epi32(-11059)), _mm256_mullo_epi32(g, _mm256_set1_epi32(-21709))),
+                                       _mm256_add_epi32(_mm256_slli_epi32(b, 15), bias));
+        __m256i vcr = _mm256_add_epi32(_mm256_add_epi32(_mm256_slli_epi32(r, 15), _mm256_mullo_epi32(g, _mm256_set1_epi32(-27439))),
+                                       _mm256_add_epi32(_mm256_mullo_epi32(b, _mm256_set1_epi32(-5329)), bias));
+        vy = _mm256_srai_epi32(vy, 16);
+        vcb = _mm256_srai_epi32(vcb, 16);
+        vcr = _mm256_srai_epi32(vcr, 16);
+        /* 8 x i32 (0..255) -> 8 bytes */
+        const __m128i y16 = _mm_packs_epi32(_mm256_castsi256_si128(vy), _mm256_extracti128_si256(vy, 1));
+        const __m128i cb16 = _mm_packs_epi32(_mm256_castsi256_si128(vcb), _mm256_extracti128_si256(vcb, 1));
+        const __m128i cr16 = _mm_packs_epi32(_mm256_castsi256_si128(vcr), _mm256_extracti128_si256(vcr, 1));
+        _mm_storel_epi64((__m128i *)(y + x), _mm_packus_epi16(y16, y16));
+        _mm_storel_epi64((__m128i *)(cb + x), _mm_packus_epi16(cb16, cb16));
+        _mm_storel_epi64((__m128i *)(cr + x), _mm_packus_epi16(cr16, cr16));
+    }
+    return x;
+}
+#endif
+
 /* ImageBuffer::fill_buffers for the nine adaptors, src/image_buffer.rs:100-313.
  * Appends `width` samples of image row y to each used plane at dst[c] and advances nothing;
  * caller owns the cursor. */
@@ -135,7 +184,11 @@ static void fill_row(const orc_params *p, const uint8_t *data, uint16_t y, uint8
     int bpp = bytes_per_pixel(p->color_type);
     const uint8_t *line = data + (size_t)y * width * bpp; /* get_line, :125-133 */
     uint8_t t[3];
-    for (size_t x = 0; x < width; x++) {
+    size_t x0 = 0;
+#if defined(__AVX2__)
+    if (g_simd && (p->color_type == ORC_RGB || p->color_type == ORC_RGBA)) x0 = rgb_row_avx2(line, width, bpp, dst[0], dst[1], dst[2]);
+#endif
+    for (size_t x = x0; x < width; x++) {
         const uint8_t *px = line + x * bpp;
         switch (p->color_type) {
         case ORC_LUMA: dst[0][x] = px[0]; break;                                   /* :115-121 */
@@ -183,7 +236,7 @@ static void fill_row(const orc_params *p, const uint8_t *data, uint16_t y, uint8
 
 static inline int32_t descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; } /* fdct.rs:94-98 */
 
-void orc_fdct(int16_t data[64]) {
+static void fdct_scalar(int16_t data[64]) {
     int32_t data2[64];
     for (int y = 0; y < 8; y++) { /* pass 1: rows, fdct.rs:116-171 */
         int o = y * 8;
@@ -230,6 +283,87 @@ void orc_fdct(int16_t data[64]) {
         data[24 + x] = (int16_t)descale(tmp6 + z2 + z3, CONST_BITS + PASS1_BITS);
         data[8 + x] = (int16_t)descale(tmp7 + z1 + z4, CONST_BITS + PASS1_BITS);
     }
+}
+
+#if defined(__AVX2__)
+/* The same LL&M flow on eight lanes of i32 (role of src/avx2/fdct.rs, which works in 16-bit lanes; i32 lanes
+ * make bit-equality with the scalar code a matter of construction). v[k] holds element k of eight independent
+ * 8-point transforms. pass 1: outputs scaled by 2^PASS1_BITS; pass 2: that scale removed again. */
+static inline __m256i vdescale(__m256i x, int n) { return _mm256_srai_epi32(_mm256_add_epi32(x, _mm256_set1_epi32(1 << (n - 1))), n); }
+#define VMUL(a, c) _mm256_mullo_epi32((a), _mm256_set1_epi32(c))
+static void dct_pass_avx2(__m256i v[8], int first) {
+    const int sh = first ? CONST_BITS - PASS1_BITS : CONST_BITS + PASS1_BITS;
+    const __m256i tmp0 = _mm256_add_epi32(v[0], v[7]), tmp7 = _mm256_sub_epi32(v[0], v[7]);
+    const __m256i tmp1 = _mm256_add_epi32(v[1], v[6]), tmp6 = _mm256_sub_epi32(v[1], v[6]);
+    const __m256i tmp2 = _mm256_add_epi32(v[2], v[5]), tmp5 = _mm256_sub_epi32(v[2], v[5]);
+    const __m256i tmp3 = _mm256_add_epi32(v[3], v[4]), tmp4 = _mm256_sub_epi32(v[3], v[4]);
+    const __m256i tmp10 = _mm256_add_epi32(tmp0, tmp3), tmp13 = _mm256_sub_epi32(tmp0, tmp3);
+    const __m256i tmp11 = _mm256_add_epi32(tmp1, tmp2), tmp12 = _mm256_sub_epi32(tmp1, tmp2);
+    if (first) {
+        v[0] = _mm256_slli_epi32(_mm256_add_epi32(tmp10, tmp11), PASS1_BITS);
+        v[4] = _mm256_slli_epi32(_mm256_sub_epi32(tmp10, tmp11), PASS1_BITS);
+    } else {
+        v[0] = vdescale(_mm256_add_epi32(tmp10, tmp11), PASS1_BITS);
+        v[4] = vdescale(_mm256_sub_epi32(tmp10, tmp11), PASS1_BITS);
+    }
+    __m256i z1 = VMUL(_mm256_add_epi32(tmp12, tmp13), FIX_0_541196100);
+    v[2] = vdescale(_mm256_add_epi32(z1, VMUL(tmp13, FIX_0_765366865)), sh);
+    v[6] = vdescale(_mm256_add_epi32(z1, VMUL(tmp12, -FIX_1_847759065)), sh);
+    z1 = _mm256_add_epi32(tmp4, tmp7);
+    __m256i z2 = _mm256_add_epi32(tmp5, tmp6), z3 = _mm256_add_epi32(tmp4, tmp6), z4 = _mm256_add_epi32(tmp5, tmp7);
+    const __m256i z5 = VMUL(_mm256_add_epi32(z3, z4), FIX_1_175875602);
+    const __m256i t4 = VMUL(tmp4, FIX_0_298631336), t5 = VMUL(tmp5, FIX_2_053119869), t6 = VMUL(tmp6, FIX_3_072711026),
+                  t7 = VMUL(tmp7, FIX_1_501321110);
+    z1 = VMUL(z1, -FIX_0_899976223);
+    z2 = VMUL(z2, -FIX_2_562915447);
+    z3 = _mm256_add_epi32(VMUL(z3, -FIX_1_961570560), z5);
+    z4 = _mm256_add_epi32(VMUL(z4, -FIX_0_390180644), z5);
+    v[7] = vdescale(_mm256_add_epi32(_mm256_add_epi32(t4, z1), z3), sh);
+    v[5] = vdescale(_mm256_add_epi32(_mm256_add_epi32(t5, z2), z4), sh);
+    v[3] = vdescale(_mm256_add_epi32(_mm256_add_epi32(t6, z2), z3), sh);
+    v[1] = vdescale(_mm256_add_epi32(_mm256_add_epi32(t7, z1), z4), sh);
+}
+static void transpose8_avx2(__m256i r[8]) {
+    const __m256i a0 = _mm256_unpacklo_epi32(r[0], r[1]), a1 = _mm256_unpackhi_epi32(r[0], r[1]);
+    const __m256i a2 = _mm256_unpacklo_epi32(r[2], r[3]), a3 = _mm256_unpackhi_epi32(r[2], r[3]);
+    const __m256i a4 = _mm256_unpacklo_epi32(r[4], r[5]), a5 = _mm256_unpackhi_epi32(r[4], r[5]);
+    const __m256i a6 = _mm256_unpacklo_epi32(r[6], r[7]), a7 = _mm256_unpackhi_epi32(r[6], r[7]);
+    const __m256i b0 = _mm256_unpacklo_epi64(a0, a2), b1 = _mm256_unpackhi_epi64(a0, a2);
+    const __m256i b2 = _mm256_unpacklo_epi64(a1, a3), b3 = _mm256_unpackhi_epi64(a1, a3);
+    const __m256i b4 = _mm256_unpacklo_epi64(a4, a6), b5 = _mm256_unpackhi_epi64(a4, a6);
+    const __m256i b6 = _mm256_unpacklo_epi64(a5, a7), b7 = _mm256_unpackhi_epi64(a5, a7);
+    r[0] = _mm256_permute2x128_si256(b0, b4, 0x20);
+    r[1] = _mm256_permute2x128_si256(b1, b5, 0x20);
+    r[2] = _mm256_permute2x128_si256(b2, b6, 0x20);
+    r[3] = _mm256_permute2x128_si256(b3, b7, 0x20);
+    r[4] = _mm256_permute2x128_si256(b0, b4, 0x31);
+    r[5] = _mm256_permute2x128_si256(b1, b5, 0x31);
+    r[6] = _mm256_permute2x128_si256(b2, b6, 0x31);
+    r[7] = _mm256_permute2x128_si256(b3, b7, 0x31);
+}
+static void fdct_avx2(int16_t data[64]) {
+    __m256i v[8];
+    for (int i = 0; i < 8; i++) v[i] = _mm256_cvtepi16_epi32(_mm_loadu_si128((const __m128i *)(data + 8 * i)));
+    transpose8_avx2(v);   /* v[k] = column k: element k of every row */
+    dct_pass_avx2(v, 1);  /* rows, fdct.rs:116-171 */
+    transpose8_avx2(v);   /* v[k] = row k of the intermediate */
+    dct_pass_avx2(v, 0);  /* columns, fdct.rs:178-237 */
+    for (int i = 0; i < 8; i++) /* results fit i16 (|v| <= 8192), so the saturating pack is the `as i16` of the scalar code */
+        _mm_storeu_si128((__m128i *)(data + 8 * i), _mm_packs_epi32(_mm256_castsi256_si128(v[i]), _mm256_extracti128_si256(v[i], 1)));
+}
+void orc_fdct_simd(int16_t data[64]) { fdct_avx2(data); }
+#else
+void orc_fdct_simd(int16_t data[64]) { fdct_scalar(data); }
+#endif
+
+void orc_fdct(int16_t data[64]) {
+#if defined(__AVX2__)
+    if (g_simd) {
+        fdct_avx2(data);
+        return;
+    }
+#endif
+    fdct_scalar(data);
 }
 
 /* 16-bit-stage model of the AVX2 backend (src/avx2/fdct.rs:258-423): every `_epi16` add/sub/shift

@@ -70,6 +70,12 @@ int orc_coefficients(const orc_params *p, const uint8_t *pixels, size_t len,
 void orc_rgb_to_ycbcr(uint8_t r, uint8_t g, uint8_t b, uint8_t out[3]);     /* image_buffer.rs:9-31 */
 void orc_fdct(int16_t block[64]);                                             /* fdct.rs:107-238 */
 void orc_fdct_i16model(int16_t block[64]);   /* 16-bit-stage model of avx2/fdct.rs:258-468 */
+void orc_fdct_simd(int16_t block[64]);       /* AVX2 fDCT (i32 lanes) when built with AVX2, else the scalar one */
+/* CPU-baseline switch: 1 = AVX2 colour conversion (Rgb/Rgba) and fDCT where the reference's `simd` feature has its
+ * own (src/avx2/ycbcr.rs, src/avx2/fdct.rs); quantizer and entropy coder stay scalar, as in the reference.
+ * Bit-identical output either way (tests/test_oracle.py). Not thread-safe to flip while encodes run. */
+void orc_set_simd(int on);
+int orc_has_simd(void);
 void orc_quant_table(uint8_t kind, const uint16_t custom[64], uint8_t quality, int luma,
                      uint16_t table[64], int32_t recip[64], int32_t corr[64]); /* quantization.rs:187-283 */
 int16_t orc_quantize(int16_t v, int32_t recip, int32_t corr);                 /* quantization.rs:291-307 */

@@ -65,6 +65,9 @@ def lib(native=False):
         l.orc_rgb_to_ycbcr.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, C.POINTER(C.c_uint8)]
         l.orc_fdct.argtypes = [C.POINTER(C.c_int16)]
         l.orc_fdct_i16model.argtypes = [C.POINTER(C.c_int16)]
+        l.orc_fdct_simd.argtypes = [C.POINTER(C.c_int16)]
+        l.orc_set_simd.argtypes = [C.c_int]
+        l.orc_has_simd.restype = C.c_int
         l.orc_quant_table.argtypes = [C.c_uint8, C.POINTER(C.c_uint16), C.c_uint8, C.c_int,
                                       C.POINTER(C.c_uint16), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         l.orc_quantize.argtypes = [C.c_int16, C.c_int32, C.c_int32]
@@ -159,9 +162,18 @@ def coefficients(data, width, height, color_type, **kw):
     return res
 
 
-def fdct(block, i16model=False):
+def set_simd(on, native=False):
+    """CPU-baseline switch (jpeg_oracle.h): AVX2 colour + fDCT like the reference's `simd` feature."""
+    lib(native).orc_set_simd(1 if on else 0)
+
+
+def has_simd(native=False):
+    return bool(lib(native).orc_has_simd())
+
+
+def fdct(block, i16model=False, simd=False):
     a = np.ascontiguousarray(block, dtype=np.int16).reshape(64).copy()
-    f = lib().orc_fdct_i16model if i16model else lib().orc_fdct
+    f = lib().orc_fdct_i16model if i16model else (lib().orc_fdct_simd if simd else lib().orc_fdct)
     f(a.ctypes.data_as(C.POINTER(C.c_int16)))
     return a
 

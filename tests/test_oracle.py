@@ -70,6 +70,33 @@ def test_fdct_avx2_model_equals_scalar():
         assert orc.fdct(b).tolist() == orc.fdct(b, i16model=True).tolist()
 
 
+def test_simd_baseline_path_is_bit_identical():
+    """The AVX2 colour conversion and fDCT that bench.py's CPU legs switch on (the role of the crate's `simd`
+    feature, src/avx2/) must not change a single bit: blocks, extremes (src/avx2/ycbcr.rs:191-237 tests the same
+    equality for colour) and whole files."""
+    if not orc.has_simd():
+        pytest.skip("oracle built without AVX2")
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        b = rng.integers(-128, 128, 64).astype(np.int16)
+        assert (orc.fdct(b) == orc.fdct(b, simd=True)).all()
+    for b in (np.full(64, -128, np.int16), np.full(64, 127, np.int16), np.tile(np.array([-128, 127], np.int16), 32)):
+        assert (orc.fdct(b) == orc.fdct(b, simd=True)).all()
+    for color, w, h, kw in (("rgb", 259, 67, dict(quality=90, sampling=(2, 2))), ("rgba", 64, 33, dict(quality=75)),
+                            ("rgb", 9, 9, dict(quality=100, sampling=(1, 1), progressive_scans=4)),
+                            ("bgr", 40, 40, dict(quality=80, optimize_huffman=True))):
+        ct = {"rgb": orc.RGB, "rgba": orc.RGBA, "bgr": orc.BGR}[color]
+        img = rng.integers(0, 256, (h, w, orc.BPP[ct]), dtype=np.uint8)
+        try:
+            orc.set_simd(False)
+            a = orc.encode(img, w, h, ct, **kw)
+            orc.set_simd(True)
+            b = orc.encode(img, w, h, ct, **kw)
+        finally:
+            orc.set_simd(False)
+        assert a == b
+
+
 def test_quant_new_100():
     """src/quantization.rs:314-338."""
     for luma in (True, False):
