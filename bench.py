@@ -163,7 +163,7 @@ class ClockSampler:
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         med = load[len(load) // 2] if load else None
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "how": "nvidia-smi every 50 ms over the timed steps plus ~1 s of the same work un-timed; median of the upper half"}
+                "how": "nvidia-smi every 50 ms from the warm-up through the timed steps plus ~1 s of the same work un-timed; median of the upper half"}
 
 
 # ---- the product arm ------------------------------------------------------------------------------
@@ -232,12 +232,15 @@ def run_product(args):
 
     # ---- device-resident timing ----
     device.set_timing(True)
-    for _ in range(args.warmup):
-        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
+    # the clock sampler (an nvidia-smi process) is started before the warm-up: its start-up initialises NVML on every
+    # GPU of the box and takes driver locks for tens of ms, which must not land inside the timed region
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    for _ in range(args.warmup):
+        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = {}
     launches = 0
@@ -455,12 +458,13 @@ def run_strips(args, rank, world, local, dev_t):
         torch.cuda.synchronize()
 
     device.set_timing(True)
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local)
-    barrier()
+    sampler = ClockSampler(local)  # started before the warm-up, see run_batch
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    for _ in range(args.warmup):
+        step()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms, launches = {}, 0
     e0.record(stream)

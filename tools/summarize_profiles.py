@@ -1,0 +1,117 @@
+"""Turns the raw output of tools/measure_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py r1f r1
+
+Reads the .ncu-rep files with `ncu -i ... --page raw --csv` (no GPU needed). Numbers taken under ncu are
+never bench values: the bench lines are copied from the un-profiled bench.py runs of the same pass.
+"""
+import collections
+import csv
+import io
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, "profiles")
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_static",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+]
+
+
+def ncu_raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    m = {}
+    for h, u, v in zip(hdr, units, vals):
+        if h in WANT or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
+            try:
+                m[h] = {"value": float(v.replace(",", "")), "unit": u}
+            except ValueError:
+                pass
+    return m, vals[hdr.index("Kernel Name")]
+
+
+def mbytes(m, key):
+    v = m[key]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v["unit"]]
+    return v["value"] * scale
+
+
+def main():
+    tag, out_tag = sys.argv[1], sys.argv[2]
+    # bench lines
+    for f in sorted(os.listdir(SRC)):
+        if f.startswith(tag + "_bench_") and f.endswith(".json"):
+            lines = [l for l in open(os.path.join(SRC, f)) if l.startswith("{")]  # torchrun / NCCL banners share stdout
+            if lines:
+                open(os.path.join(DST, out_tag + f[len(tag):]), "w").write(lines[-1])
+    for f in ("compute_sanitizer_memcheck.txt", "compute_sanitizer_racecheck.txt", "launches_c3_b64.csv"):
+        p = os.path.join(SRC, "%s_%s" % (tag, f))
+        if os.path.exists(p):
+            shutil.copy(p, os.path.join(DST, "%s_%s" % (out_tag, f)))
+    # launch list
+    p = os.path.join(SRC, tag + "_launches_c3_b64.csv")
+    if os.path.exists(p):
+        rows = list(csv.reader(open(p)))
+        hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+        hdr = rows[hi]
+        kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        agg = collections.defaultdict(list)
+        for r in rows[hi + 1:]:
+            if len(r) <= mv:
+                continue
+            v = float(r[mv].replace(",", ""))
+            v = v / 1000 if r[mu] == "ns" else (v * 1000 if r[mu] == "ms" else v)
+            agg[re.sub(r"\(.*", "", r[kn]).replace("jpgb::<unnamed>::", "").replace("void ", "")[:48]].append(v)
+        tot = sum(sum(v) for v in agg.values())
+        with open(os.path.join(DST, out_tag + "_launches_c3_b64_summary.txt"), "w") as f:
+            f.write("ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu\n")
+            f.write("(all launches of the process: parity gate, warm-up, timed steps and the chunked e2e calls; cold-cache and serialised,\n"
+                    " so only the SHARES are comparable with the live stage timers of the bench line)\n")
+            for k, v in sorted(agg.items(), key=lambda x: -sum(x[1])):
+                f.write("%-50s n=%3d %10.1f us %5.1f%%  largest launch %8.1f us\n" % (k, len(v), sum(v), 100 * sum(v) / tot, max(v)))
+    # full captures
+    frames = 64
+    alg = 1920 * 1080 * 3 + 128 * 48960
+    rep = os.path.join(SRC, tag + "_stage_a.ncu-rep")
+    if os.path.exists(rep):
+        m, name = ncu_raw(rep)
+        tr = mbytes(m, "dram__bytes_read.sum") + mbytes(m, "dram__bytes_write.sum")
+        s = {"kernel": name, "command": "ncu --set full --clock-control none --import-source on -k regex:stage_a_warp -s 2 -c 1 "
+             "python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu", "frames_per_launch": frames,
+             "dram_bytes_per_launch": tr, "dram_bytes_per_frame": tr / frames, "algorithmic_bytes_per_frame": alg, "metrics": m,
+             "sass": "UTMALDG.3D (TMA), SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier), IDP.2A (colour), STG.E.ENL2.256 (stores): "
+                     "cuobjdump -sass jpeg_encoder_b200/build/stage_a.cu.o",
+             "note": "cold-cache single launch under ncu; the bench line's roofline.achieved uses the live CUDA-event time of the 1024-frame launch"}
+        json.dump(s, open(os.path.join(DST, out_tag + "_stage_a_ncu_summary.json"), "w"), indent=1)
+        json.dump({"workload": "c3", "dram_bytes_per_frame": tr / frames, "source": "profiles/%s_stage_a_ncu_summary.json" % out_tag},
+                  open(os.path.join(DST, "stage_a_traffic.json"), "w"), indent=1)
+    rep = os.path.join(SRC, tag + "_encode.ncu-rep")
+    if os.path.exists(rep):
+        m, name = ncu_raw(rep)
+        visits = frames * 48960
+        s = {"kernel": name, "command": "ncu --set full --clock-control none --import-source on -k regex:encode_visits -s 2 -c 1 "
+             "python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu", "frames_per_launch": frames, "visits_per_launch": visits,
+             "warp_instructions_per_warp_of_32_visits": m["smsp__inst_executed.sum"]["value"] / (visits / 32),
+             "algorithmic_bytes_per_frame": 128 * 48960, "metrics": m,
+             "note": "bound by the ALU pipe / instruction issue, not by HBM: see DESIGN.md section 4 (stage B)"}
+        json.dump(s, open(os.path.join(DST, out_tag + "_encode_ncu_summary.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
