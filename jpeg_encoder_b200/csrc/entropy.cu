@@ -32,6 +32,7 @@ struct VisitInfo {
     const int16_t *blk;   // this block's 64 zig-zag coefficients
     const int16_t *pred;  // block holding the DC predictor, or nullptr for "predictor is 0"
     int comp, ss, se, tbl;
+    int pred_back;        // the predecessor block is the block of visit (this - pred_back)
     unsigned long long first_visit_of_seg; // within the image
     unsigned seg_local;                    // segment index within the image
     unsigned seg_in_scan;
@@ -107,6 +108,7 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
         divmod(unit, P.div_mcu_cols, my, mx);
         const unsigned long long off = P.comp_off[comp];
         blk = off + (unsigned long long)(my * V + bv) * pw + mx * H + bh;
+        r.pred_back = (bh > 0 || bv > 0) ? 1 : (int)(S.bpu - H * V + 1);
         if (bh > 0) pred = blk - 1;
         else if (bv > 0) pred = off + (unsigned long long)(my * V + bv - 1) * pw + mx * H + (H - 1);
         else if (restart_here) has_pred = false;
@@ -116,6 +118,7 @@ __device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_
         }
     } else {
         comp = S.comp;
+        r.pred_back = 1;
         const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
         const unsigned long long off = P.comp_off[comp];
         unsigned by, bx;
@@ -372,17 +375,19 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
             m_lo = __brev((unsigned)m); // coded from the highest bit down
             m_hi = __brev((unsigned)(m >> 32));
         }
-        if (FULL || vi.ss == 0) { // write_dc, writer.rs:342-352
-            const int dc = sh.coef[tid * kStageStride];
-            const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
-            int size;
-            uint32_t bits;
-            value_code((int)(int16_t)(dc - prev), size, bits);
-            first = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
-        }
     }
     const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
     __syncthreads();
+    if (valid && (FULL || vi.ss == 0)) { // write_dc, writer.rs:342-352
+        // The predecessor is the block of an earlier visit of this scan, a few visits back: staged by this CTA
+        // (all staging is complete after the barrier) unless this visit is among the CTA's first.
+        const int dc = sh.coef[tid * kStageStride];
+        const int prev = !vi.pred ? 0 : (tid >= vi.pred_back ? (int)sh.coef[(tid - vi.pred_back) * kStageStride] : (int)__ldg(vi.pred));
+        int size;
+        uint32_t bits;
+        value_code((int)(int16_t)(dc - prev), size, bits);
+        first = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
+    }
     const unsigned rank = atomicAdd(&sh.bin[nnz], 1u);
     sh.ptr_or_mask[tid] = ((unsigned long long)m_hi << 32) | m_lo;
     sh.first[tid] = first;
