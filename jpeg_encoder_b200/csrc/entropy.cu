@@ -208,6 +208,7 @@ struct __align__(16) EncodeShared {
     uint32_t first[kEncThreads];  // the DC code of the visit (table-word format), 0 in AC scans
     uint32_t info[kEncThreads];   // se | first_ac << 8 | table << 16 | valid << 24
     uint32_t ac_tab[2 * 256];
+    uint32_t dc_tab[2 * 16];
     uint32_t bin[64];
     uint16_t order[kEncThreads];
 };
@@ -301,9 +302,15 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
         split_visit(P, (cta_base + kEncThreads < n_visits ? cta_base + kEncThreads : n_visits) - 1, img_last, tmp);
     }
     const bool shared_tables = img_first == img_last;
+    // the table words travel through registers: loaded here, stored to shared memory just before the first CTA
+    // barrier, so their latency hides behind locating and staging
+    static_assert(kEncThreads == 256, "two AC words and at most one DC word per thread");
+    uint32_t tab_ac0 = 0, tab_ac1 = 0, tab_dc = 0;
     if (shared_tables) {
         const uint32_t *set = b.huff + img_first * kHuffWordsPerImage;
-        for (int i = tid; i < 512; i += kEncThreads) sh.ac_tab[i] = __ldg(set + (i >> 8) * 512 + 256 + (i & 255));
+        tab_ac0 = __ldg(set + 256 + tid);       // table 0, AC
+        tab_ac1 = __ldg(set + 512 + 256 + tid); // table 1, AC
+        if (tid < 32) tab_dc = __ldg(set + (tid >> 4) * 512 + (tid & 15)); // DC categories 0..15 of both tables
     }
     if (tid < 64) sh.bin[tid] = 0;
 
@@ -377,6 +384,11 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
         }
     }
     const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
+    if (shared_tables) {
+        sh.ac_tab[tid] = tab_ac0;
+        sh.ac_tab[256 + tid] = tab_ac1;
+        if (tid < 32) sh.dc_tab[tid] = tab_dc;
+    }
     __syncthreads();
     if (valid && (FULL || vi.ss == 0)) { // write_dc, writer.rs:342-352
         // The predecessor is the block of an earlier visit of this scan, a few visits back: staged by this CTA
@@ -386,14 +398,14 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
         int size;
         uint32_t bits;
         value_code((int)(int16_t)(dc - prev), size, bits);
-        first = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
+        first = (shared_tables ? sh.dc_tab[vi.tbl * 16 + size] : __ldg(huff_for(b, img, vi.tbl, 0) + size)) | bits;
     }
     const unsigned rank = atomicAdd(&sh.bin[nnz], 1u);
     sh.ptr_or_mask[tid] = ((unsigned long long)m_hi << 32) | m_lo;
     sh.first[tid] = first;
     sh.info[tid] = (unsigned)vi.se | ((unsigned)first_ac << 8) | ((unsigned)vi.tbl << 16) | (valid ? 1u << 24 : 0u);
     __syncthreads();
-    if (warp == 0) { // exclusive prefix over the 64 bins, two per lane
+    { // exclusive prefix over the 64 bins, two per lane; every warp computes it for itself (no single-warp step)
         const unsigned a = sh.bin[2 * lane], c = sh.bin[2 * lane + 1];
         unsigned inc = a + c;
 #pragma unroll
@@ -401,11 +413,10 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
             const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += o;
         }
-        sh.bin[2 * lane] = inc - a - c;
-        sh.bin[2 * lane + 1] = inc - c;
+        const unsigned even = inc - a - c, odd = inc - c; // first rank of bins 2*lane and 2*lane + 1
+        const unsigned e = __shfl_sync(0xffffffffu, even, nnz >> 1), o = __shfl_sync(0xffffffffu, odd, nnz >> 1);
+        sh.order[((nnz & 1) ? o : e) + rank] = (uint16_t)tid;
     }
-    __syncthreads();
-    sh.order[sh.bin[nnz] + rank] = (uint16_t)tid;
     __syncthreads();
 
     // ---- 3. code the visit of rank tid ----
