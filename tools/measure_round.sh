@@ -28,5 +28,5 @@ ncu --set full --clock-control none --import-source on -k regex:encode_visits -s
 SUB='reference_rgb or sampling_factors or progressive_scan or restart_intervals or strips or stream_exact or planes or ragged'
 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -k "$SUB" > $O/${TAG}_compute_sanitizer_memcheck.txt 2>&1
 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -k "reference_rgb or progressive_scan or restart_intervals or strips" > $O/${TAG}_compute_sanitizer_racecheck.txt 2>&1
-tail -3 $O/${TAG}_compute_sanitizer_memcheck.txt $O/${TAG}_compute_sanitizer_racecheck.txt
+tail -n 3 $O/${TAG}_compute_sanitizer_memcheck.txt; tail -n 3 $O/${TAG}_compute_sanitizer_racecheck.txt
 cut -c1-300 $O/${TAG}_bench_c3_1gpu.json
