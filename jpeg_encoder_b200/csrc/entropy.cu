@@ -599,15 +599,27 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
 
 // ---- 0xFF stuffing (writer.rs:156-167) as count / scan / scatter ---------------------------------
 // A thread owns 16 consecutive bytes of the unstuffed stream and the 16 raw_mask bits beside them.
+// 0x80 in every byte of w that equals 0xFF, exact (no carries cross bytes): a byte of ~w is zero iff neither its
+// low seven bits (sum with 0x7F stays below 0x80) nor its top bit are set.
+__device__ __forceinline__ uint32_t ff_flags(uint32_t w) {
+    const uint32_t x = ~w;
+    const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+    return ~t & 0x80808080u;
+}
+// flags at bits 7, 15, 23, 31 -> bits 0..3 (the four products land on distinct bits 21..24)
+__device__ __forceinline__ unsigned flags_to_nibble(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
 __device__ __forceinline__ unsigned ff_bits16(const uint4 d, unsigned raw16, unsigned valid) {
-    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-    unsigned m = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu) == 0xFFu) m |= 1u << i;
+    unsigned m = flags_to_nibble(ff_flags(d.x)) | flags_to_nibble(ff_flags(d.y)) << 4 | flags_to_nibble(ff_flags(d.z)) << 8 |
+                 flags_to_nibble(ff_flags(d.w)) << 12;
     m &= ~raw16;
     if (valid < 16) m &= (1u << valid) - 1u;
     return m;
+}
+// number of data 0xFF bytes among the 16 (same as popc(ff_bits16), cheaper when nothing is raw)
+__device__ __forceinline__ unsigned ff_count16(const uint4 d, unsigned raw16, unsigned valid) {
+    if (raw16 == 0 && valid >= 16) return __popc(ff_flags(d.x)) + __popc(ff_flags(d.y)) + __popc(ff_flags(d.z)) + __popc(ff_flags(d.w));
+    return __popc(ff_bits16(d, raw16, valid));
 }
 
 __global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b) {
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b) {
         const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + base);
         const unsigned raw = (b.raw_mask[base >> 5] >> (base & 31)) & 0xFFFFu;
         const unsigned valid = bytes - base < 16 ? (unsigned)(bytes - base) : 16u;
-        cnt = __popc(ff_bits16(d, raw, valid));
+        cnt = ff_count16(d, raw, valid);
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
@@ -707,7 +719,7 @@ __device__ __forceinline__ unsigned ff_before_in_chunk(const EntropyBuffers &b, 
         const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + i);
         const unsigned raw = (b.raw_mask[i >> 5] >> (i & 31)) & 0xFFFFu;
         const unsigned valid = pos - i < 16 ? (unsigned)(pos - i) : 16u;
-        ff += __popc(ff_bits16(d, raw, valid));
+        ff += ff_count16(d, raw, valid);
     }
     return __reduce_add_sync(0xffffffffu, ff);
 }
