@@ -539,19 +539,29 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     split_visit(P, g, img, v);
     unsigned nb = b.nbits[g];
     // segment bookkeeping only (no coefficient access)
-    const int k = find_scan_by_visit(P, v);
-    const DevScan &S = P.scans[k];
-    unsigned unit, slot_in_unit;
-    split_unit(S, v, unit, slot_in_unit);
-    const unsigned R = (unsigned)P.restart;
-    unsigned seg_in_scan = 0, seg_r = unit;
-    if (R) divmod(unit, P.div_restart, seg_in_scan, seg_r);
-    const bool last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
-    if (nb == 0 && !last_of_seg) return;
-    const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
-    const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
-    const unsigned long long data_byte = b.segpos[seg] + lead_len(b, P, img, k, seg_in_scan);
-    const unsigned long long rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + first_visit];
+    bool last_of_seg;
+    unsigned long long data_byte, rel_bits;
+    if (P.n_scans == 1 && P.restart == 0 && P.scans[0].rst_base == 0) {
+        // one scan, no restarts (the interleaved baseline file): the image is one segment that starts with the header
+        last_of_seg = v == P.visits_per_image - 1;
+        if (nb == 0 && !last_of_seg) return;
+        data_byte = b.segpos[img] + b.hdr_len[b.huff_per_image ? img : 0];
+        rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image];
+    } else {
+        const int k = find_scan_by_visit(P, v);
+        const DevScan &S = P.scans[k];
+        unsigned unit, slot_in_unit;
+        split_unit(S, v, unit, slot_in_unit);
+        const unsigned R = (unsigned)P.restart;
+        unsigned seg_in_scan = 0, seg_r = unit;
+        if (R) divmod(unit, P.div_restart, seg_in_scan, seg_r);
+        last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
+        if (nb == 0 && !last_of_seg) return;
+        const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
+        const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
+        data_byte = b.segpos[seg] + lead_len(b, P, img, k, seg_in_scan);
+        rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + first_visit];
+    }
     const unsigned long long bitpos = data_byte * 8 + rel_bits;
 
     uint32_t *dst = reinterpret_cast<uint32_t *>(b.ustream) + (bitpos >> 5);
