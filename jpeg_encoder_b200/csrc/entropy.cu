@@ -535,6 +535,13 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_visits || !stream_fits(b)) return;
     const DevPlan &P = *b.plan;
+    // The kernel is bound by the latency of its dependent loads, not by bytes or instructions: the first four slot
+    // words are requested before anything else is known (every visit owns all kSlotWords rows of its tile, so the
+    // loads are always in bounds; words beyond the visit's code are simply not used).
+    const uint32_t *src = slot_of(b.slots, g);
+    uint32_t pre[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pre[q] = src[(size_t)q * kSlotTile];
     unsigned long long img, v;
     split_visit(P, g, img, v);
     unsigned nb = b.nbits[g];
@@ -567,7 +574,6 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     uint32_t *dst = reinterpret_cast<uint32_t *>(b.ustream) + (bitpos >> 5);
     const unsigned sh = (unsigned)(bitpos & 31);
     const unsigned n_words = (nb + 31) >> 5;
-    const uint32_t *src = slot_of(b.slots, g);
     unsigned pad = 0;
     if (last_of_seg) {
         const unsigned end_bits = (unsigned)((rel_bits + nb) & 7);
@@ -575,8 +581,7 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
     }
     uint32_t carry = 0; // bits still to be written into the current destination word (left-aligned)
     bool first = true;
-    for (unsigned j = 0; j < n_words; ++j) {
-        uint32_t w = src[j * kSlotTile];
+    auto emit = [&](unsigned j, uint32_t w) {
         const unsigned have = (j + 1 == n_words) ? nb - 32 * j : 32u; // valid bits in w (left-aligned)
         if (j + 1 == n_words && pad) { // append the pad ones behind the last code bits when they fit in this word
             if (have + pad <= 32) {
@@ -598,7 +603,11 @@ __global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b,
                 if (spill) atomicOr(dst, __byte_perm(carry, 0, 0x0123));
             }
         }
-    }
+    };
+#pragma unroll
+    for (unsigned j = 0; j < 4; ++j)
+        if (j < n_words) emit(j, pre[j]);
+    for (unsigned j = 4; j < n_words; ++j) emit(j, src[(size_t)j * kSlotTile]);
     if (pad) { // pad bits that did not fit next to the last code word (or a visit without bits)
         const unsigned long long p = bitpos + nb;
         uint32_t *d2 = reinterpret_cast<uint32_t *>(b.ustream) + (p >> 5);
