@@ -216,3 +216,41 @@ if _HAVE_HYPOTHESIS:
             # combination may fail. (The fixed CASES above cover optimized + restart inputs that do not hit Q18.)
             if not (cfg.get("optimize_huffman") and cfg.get("restart_interval")):
                 raise
+
+
+# ---- the checker checked: the T.81 decoder reads files of an unrelated encoder (libjpeg via PIL) ----------------
+def _idct_plane(d, c):
+    """Dequantize + float IDCT of component c -> (rows, cols) samples (T.81 A.3.3), for comparison with libjpeg's decode."""
+    _, hs, vs, tq = d.components[c]
+    q = np.array(d.qt[tq][1], np.float64)
+    coef = d.coef[c].astype(np.float64) * q            # zig-zag order
+    nat = np.zeros_like(coef)
+    nat[..., ZIGZAG] = coef                             # position i of the zig-zag sequence is natural index ZIGZAG[i]
+    blocks = nat.reshape(coef.shape[0], coef.shape[1], 8, 8)
+    k = np.arange(8)
+    basis = np.cos((2 * k[None, :] + 1) * k[:, None] * np.pi / 16) * np.where(k[:, None] == 0, np.sqrt(0.5), 1.0) * 0.5  # [u][x]
+    px = np.einsum("uy,abuv,vx->abyx", basis, blocks, basis) + 128.0
+    return px.transpose(0, 2, 1, 3).reshape(coef.shape[0] * 8, coef.shape[1] * 8)
+
+
+@pytest.mark.parametrize("mode,kw", [("L", dict(quality=90)), ("L", dict(quality=60, optimize=True)),
+                                     ("RGB", dict(quality=85, subsampling=0)), ("RGB", dict(quality=75, subsampling=2, optimize=True))])
+def test_t81_decoder_reads_libjpeg_files(mode, kw):
+    import io
+    from PIL import Image
+    w, h = 93, 61
+    img = images.photo_like(w, h, 1 if mode == "L" else 3, seed=5)
+    buf = io.BytesIO()
+    Image.fromarray(img.reshape(h, w) if mode == "L" else img.reshape(h, w, 3), mode).save(buf, "JPEG", **kw)
+    d = t81.decode(buf.getvalue())
+    assert (d.width, d.height) == (w, h) and not d.progressive
+    im = Image.open(io.BytesIO(buf.getvalue()))
+    if mode == "RGB":
+        im.draft("YCbCr", im.size)  # libjpeg's samples before colour conversion
+        assert im.mode == "YCbCr"
+    ref = np.asarray(im).astype(np.float64)
+    ref = ref[..., None] if ref.ndim == 2 else ref
+    n = 1 if mode == "L" or kw.get("subsampling") else 3  # subsampled chroma is upsampled by libjpeg: compare luma only
+    for c in range(n):
+        mine = _idct_plane(d, c)[:h, :w]
+        assert np.abs(np.clip(np.rint(mine), 0, 255) - ref[..., c]).max() <= 2  # libjpeg's integer IDCT vs float
