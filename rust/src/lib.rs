@@ -27,6 +27,26 @@ extern "C" {
     fn jpgb_encoder_destroy(enc: *mut JpgbEncoder);
     fn jpgb_encode_to_sink(enc: *mut JpgbEncoder, p: *const JpgbParams, pixels: *const u8, len: usize,
                            write_all: WriteAll, user: *mut c_void) -> c_int;
+    fn jpgb_encode_planar(enc: *mut JpgbEncoder, p: *const JpgbParams, planes: *const *const u8, plane_len: usize,
+                          out: *mut *mut u8, out_len: *mut usize) -> c_int;
+    fn jpgb_free(buf: *mut c_void);
+}
+
+/// src/encoder.rs:27-65
+#[derive(Copy, Clone, Debug, Eq, PartialEq)]
+pub enum JpegColorType { Luma, Ycbcr, Cmyk, Ycck }
+impl JpegColorType {
+    fn get_num_components(self) -> usize { match self { JpegColorType::Luma => 1, JpegColorType::Ycbcr => 3, _ => 4 } }
+    /// the C ABI's colour code of the matching verbatim input type (JPGB_LUMA / YCBCR / CMYK / YCCK)
+    fn abi_code(self) -> u8 { match self { JpegColorType::Luma => 0, JpegColorType::Ycbcr => 5, JpegColorType::Cmyk => 6, JpegColorType::Ycck => 8 } }
+}
+
+/// src/image_buffer.rs:86-98: a user pixel format. `fill_buffers` appends one row of converted samples per component.
+pub trait ImageBuffer {
+    fn get_jpeg_color_type(&self) -> JpegColorType;
+    fn width(&self) -> u16;
+    fn height(&self) -> u16;
+    fn fill_buffers(&self, y: u16, buffers: &mut [Vec<u8>; 4]);
 }
 
 #[derive(Copy, Clone, Debug, Eq, PartialEq)]
@@ -126,35 +146,74 @@ impl<W: JfifWrite> Encoder<W> {
         let mut f = vec![0x45, 0x78, 0x69, 0x66, 0x00, 0x00]; f.extend_from_slice(data); self.add_app_segment(1, f)
     }
 
-    /// Encoder::encode: same contract as the reference; the work runs on the B200.
+    /// The state of this encoder as the C ABI takes it (`apps` must outlive the returned struct).
+    unsafe fn params(&self, width: u16, height: u16, color_code: u8, apps: &[JpgbApp]) -> JpgbParams {
+        let mut p: JpgbParams = std::mem::zeroed();
+        jpgb_params_default(&mut p, self.quality);
+        p.width = width; p.height = height; p.color_type = color_code; p.sampling = self.sampling as u8;
+        for i in 0..2 {
+            p.qtable_kind[i] = self.tables[i].kind();
+            if let QuantizationTableType::Custom(t) = &self.tables[i] { p.qtable_custom[i] = **t; }
+        }
+        p.progressive_scans = self.progressive_scans.unwrap_or(0);
+        p.optimize_huffman = self.optimize as u8;
+        p.restart_interval = self.restart_interval.unwrap_or(0);
+        p.density_unit = match self.density.unit { PixelDensityUnit::PixelAspectRatio => 0, PixelDensityUnit::Inches => 1, PixelDensityUnit::Centimeters => 2 };
+        p.density_x = self.density.density.0; p.density_y = self.density.density.1;
+        p.n_app = apps.len() as u32; p.apps = apps.as_ptr();
+        p
+    }
+
+    /// One encoder context (CUDA stream + device buffers) per host thread; there is no CPU fallback.
+    unsafe fn context() -> Result<*mut JpgbEncoder, EncodingError> {
+        thread_local! { static CTX: std::cell::Cell<*mut JpgbEncoder> = std::cell::Cell::new(std::ptr::null_mut()); }
+        let ctx = CTX.with(|c| { if c.get().is_null() { let mut e = std::ptr::null_mut(); if jpgb_encoder_create(0, std::ptr::null_mut(), &mut e) == 0 { c.set(e); } } c.get() });
+        if ctx.is_null() { Err(EncodingError::Cuda(8)) } else { Ok(ctx) }
+    }
+
+    /// Encoder::encode (src/encoder.rs:440-503): same contract as the reference; the work runs on the B200.
     pub fn encode(mut self, data: &[u8], width: u16, height: u16, color_type: ColorType) -> Result<(), EncodingError> {
         let required = width as usize * height as usize * color_type.bpp();
         if data.len() < required { return Err(EncodingError::BadImageData { length: data.len(), required }); }
         if width == 0 || height == 0 { return Err(EncodingError::ZeroImageDimensions { width, height }); }
         let apps: Vec<JpgbApp> = self.apps.iter().map(|(nr, d)| JpgbApp { nr: *nr, data: d.as_ptr(), len: d.len() as u32 }).collect();
         unsafe {
-            let mut p: JpgbParams = std::mem::zeroed();
-            jpgb_params_default(&mut p, self.quality);
-            p.width = width; p.height = height; p.color_type = color_type as u8; p.sampling = self.sampling as u8;
-            for i in 0..2 {
-                p.qtable_kind[i] = self.tables[i].kind();
-                if let QuantizationTableType::Custom(t) = &self.tables[i] { p.qtable_custom[i] = **t; }
-            }
-            p.progressive_scans = self.progressive_scans.unwrap_or(0);
-            p.optimize_huffman = self.optimize as u8;
-            p.restart_interval = self.restart_interval.unwrap_or(0);
-            p.density_unit = match self.density.unit { PixelDensityUnit::PixelAspectRatio => 0, PixelDensityUnit::Inches => 1, PixelDensityUnit::Centimeters => 2 };
-            p.density_x = self.density.density.0; p.density_y = self.density.density.1;
-            p.n_app = apps.len() as u32; p.apps = apps.as_ptr();
-            thread_local! { static CTX: std::cell::Cell<*mut JpgbEncoder> = std::cell::Cell::new(std::ptr::null_mut()); }
-            let ctx = CTX.with(|c| { if c.get().is_null() { let mut e = std::ptr::null_mut(); if jpgb_encoder_create(0, std::ptr::null_mut(), &mut e) == 0 { c.set(e); } } c.get() });
-            if ctx.is_null() { return Err(EncodingError::Cuda(8)); }
+            let p = self.params(width, height, color_type as u8, &apps);
+            let ctx = Self::context()?;
             let mut st = SinkState { w: &mut self.w, err: None };
             let rc = jpgb_encode_to_sink(ctx, &p, data.as_ptr(), data.len(), sink_trampoline::<W>, &mut st as *mut _ as *mut c_void);
             if let Some(e) = st.err { return Err(e); }
             if rc != 0 { return Err(EncodingError::Cuda(rc)); }
         }
         Ok(())
+    }
+
+    /// Encoder::encode_image (src/encoder.rs:506-515): the user's `fill_buffers` runs on the host, row by row, exactly as
+    /// the reference calls it; the GPU takes the resulting planes as already-converted component samples
+    /// (jpgb_encode_planar) and does padding, decimation, fDCT, quantization and entropy coding.
+    pub fn encode_image<I: ImageBuffer>(mut self, image: I) -> Result<(), EncodingError> {
+        let (width, height) = (image.width(), image.height());
+        if width == 0 || height == 0 { return Err(EncodingError::ZeroImageDimensions { width, height }); }
+        let jct = image.get_jpeg_color_type();
+        let mut planes: [Vec<u8>; 4] = Default::default();
+        for y in 0..height { image.fill_buffers(y, &mut planes); }
+        let plane_len = width as usize * height as usize;
+        let n = jct.get_num_components();
+        if planes[..n].iter().any(|pl| pl.len() < plane_len) {
+            return Err(EncodingError::BadImageData { length: planes[..n].iter().map(|pl| pl.len()).min().unwrap_or(0), required: plane_len });
+        }
+        let ptrs: [*const u8; 4] = [planes[0].as_ptr(), planes[1].as_ptr(), planes[2].as_ptr(), planes[3].as_ptr()];
+        let apps: Vec<JpgbApp> = self.apps.iter().map(|(nr, d)| JpgbApp { nr: *nr, data: d.as_ptr(), len: d.len() as u32 }).collect();
+        unsafe {
+            let p = self.params(width, height, jct.abi_code(), &apps);
+            let ctx = Self::context()?;
+            let (mut out, mut out_len) = (std::ptr::null_mut::<u8>(), 0usize);
+            let rc = jpgb_encode_planar(ctx, &p, ptrs.as_ptr(), plane_len, &mut out, &mut out_len);
+            if rc != 0 { return Err(EncodingError::Cuda(rc)); }
+            let res = self.w.write_all(std::slice::from_raw_parts(out, out_len));
+            jpgb_free(out as *mut c_void);
+            res
+        }
     }
 }
 #[allow(dead_code)] fn _keep(e: *mut JpgbEncoder) { unsafe { jpgb_encoder_destroy(e) } }
