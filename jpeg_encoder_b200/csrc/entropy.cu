@@ -329,13 +329,18 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
     }
     if (!FULL && !__syncthreads_or(valid && vi.se > 0)) { // a CTA inside DC scans (progressive): one code per visit
         if (valid) {
-            const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
-            int size;
-            uint32_t bits;
-            value_code((int)(int16_t)(__ldg(vi.blk) - prev), size, bits);
-            const uint32_t e = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
-            const unsigned len = e >> 27;
-            if (len) *slot_of(b.slots, g) = (e & kCodeBits) << (32 - len);
+            unsigned len = 0;
+            // se == 0 is a DC scan (ss == 0) or the *empty* first AC band that 34..64 progressive scans produce
+            // (64 / (scans - 1) == 1: band 0 = [1, 1), written as Ss=1, Se=0 -- encoder.rs:926-944): no bits at all
+            if (vi.ss == 0) {
+                const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
+                int size;
+                uint32_t bits;
+                value_code((int)(int16_t)(__ldg(vi.blk) - prev), size, bits);
+                const uint32_t e = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
+                len = e >> 27;
+                if (len) *slot_of(b.slots, g) = (e & kCodeBits) << (32 - len);
+            }
             b.nbits[g] = len;
         }
         return;

@@ -424,3 +424,48 @@ def test_concurrent_contexts_on_threads():
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+# ---- randomized sweep over the whole settings space (seeded: the same 96 cases every run) -----------------------
+def _random_cases(n=96, seed=20260117):
+    rng = np.random.default_rng(seed)
+    colors = sorted(BPP)
+    samplings = [(1, 1), (2, 1), (1, 2), (2, 2), (4, 1), (4, 2), (1, 4), (2, 4)]
+    out = []
+    for i in range(n):
+        color = colors[int(rng.integers(len(colors)))]
+        w, h = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        cfg = dict(quality=int(rng.integers(1, 101)), sampling=samplings[int(rng.integers(len(samplings)))])
+        if rng.random() < 0.4:
+            cfg["progressive_scans"] = int(rng.integers(2, 65))
+        if rng.random() < 0.5:
+            cfg["restart_interval"] = int(rng.integers(1, 60))
+        if rng.random() < 0.4:
+            cfg["optimize_huffman"] = True
+        r = rng.random()
+        if r < 0.3:
+            cfg["qtables"] = (int(rng.integers(0, 9)), int(rng.integers(0, 9)))
+        elif r < 0.45:
+            cfg["qtables"] = ([int(v) for v in rng.integers(1, 300, 64)], [int(v) for v in rng.integers(1, 40, 64)])
+        kind = ["photo", "noise", "flat"][int(rng.integers(3))]
+        out.append((i, color, w, h, cfg, kind))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", range(8))
+def test_random_settings_sweep(chunk):
+    """96 seeded random combinations of colour type, geometry, quality, sampling, tables, progressive scan count,
+    restart interval and optimized tables (including the Q18 inputs whose streams are knowingly undecodable): the GPU
+    file must equal the oracle's byte for byte."""
+    for i, color, w, h, cfg, kind in _random_cases()[chunk::8]:
+        rng = np.random.default_rng(1000 + i)
+        if kind == "photo":
+            img = _img(color, w, h, seed=i)
+        elif kind == "noise":
+            img = rng.integers(0, 256, (h, w, BPP[color]), dtype=np.uint8)
+        else:
+            img = np.full((h, w, BPP[color]), int(rng.integers(0, 256)), np.uint8)
+        got = gpu_encode(img, w, h, color, cfg)
+        want = oracle_encode(img, w, h, color, cfg)
+        assert got == want, "case %d: %s %dx%d %r (%s): %d vs %d bytes" % (i, color, w, h, {k: v for k, v in cfg.items() if k != "qtables"}, kind, len(got), len(want))
