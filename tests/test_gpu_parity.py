@@ -427,14 +427,18 @@ def test_concurrent_contexts_on_threads():
 
 
 # ---- randomized sweep over the whole settings space (seeded: the same 96 cases every run) -----------------------
-def _random_cases(n=96, seed=20260117):
+def _random_cases(n=None, seed=None):
+    import os
+    n = int(os.environ.get("JPGB_SWEEP_CASES", "96")) if n is None else n       # a longer hunt: JPGB_SWEEP_CASES=2000
+    seed = int(os.environ.get("JPGB_SWEEP_SEED", "20260117")) if seed is None else seed
+    max_dim = int(os.environ.get("JPGB_SWEEP_MAXDIM", "120"))
     rng = np.random.default_rng(seed)
     colors = sorted(BPP)
     samplings = [(1, 1), (2, 1), (1, 2), (2, 2), (4, 1), (4, 2), (1, 4), (2, 4)]
     out = []
     for i in range(n):
         color = colors[int(rng.integers(len(colors)))]
-        w, h = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        w, h = int(rng.integers(1, max_dim)), int(rng.integers(1, max_dim))
         cfg = dict(quality=int(rng.integers(1, 101)), sampling=samplings[int(rng.integers(len(samplings)))])
         if rng.random() < 0.4:
             cfg["progressive_scans"] = int(rng.integers(2, 65))
@@ -458,6 +462,7 @@ def test_random_settings_sweep(chunk):
     """96 seeded random combinations of colour type, geometry, quality, sampling, tables, progressive scan count,
     restart interval and optimized tables (including the Q18 inputs whose streams are knowingly undecodable): the GPU
     file must equal the oracle's byte for byte."""
+    failures = []
     for i, color, w, h, cfg, kind in _random_cases()[chunk::8]:
         rng = np.random.default_rng(1000 + i)
         if kind == "photo":
@@ -468,4 +473,7 @@ def test_random_settings_sweep(chunk):
             img = np.full((h, w, BPP[color]), int(rng.integers(0, 256)), np.uint8)
         got = gpu_encode(img, w, h, color, cfg)
         want = oracle_encode(img, w, h, color, cfg)
-        assert got == want, "case %d: %s %dx%d %r (%s): %d vs %d bytes" % (i, color, w, h, {k: v for k, v in cfg.items() if k != "qtables"}, kind, len(got), len(want))
+        if got != want:
+            failures.append("case %d: %s %dx%d %r (%s): %d vs %d bytes" % (i, color, w, h, {k: v for k, v in cfg.items() if k != "qtables"},
+                                                                           kind, len(got), len(want)))
+    assert not failures, "\n".join(failures)
