@@ -91,7 +91,8 @@ class Decoded:
     counts how many scans touched each (block, coefficient)."""
 
 
-def decode(jpg):
+def decode(jpg, headers_only=False):
+    """headers_only: stop at the first SOS (tables and frame parameters only)."""
     jpg = bytes(jpg)
     r = Decoded()
     r.segments, r.apps, r.qt, r.scans = [], [], {}, []
@@ -173,6 +174,8 @@ def decode(jpg):
             r.segments.append("SOS")
             if frame is None:
                 raise JpegSyntaxError("SOS before SOF")
+            if headers_only:
+                return r
             ns = body[0]
             sel = [(body[1 + 2 * k], body[2 + 2 * k] >> 4, body[2 + 2 * k] & 15) for k in range(ns)]
             ss, se, ahal = body[1 + 2 * ns], body[2 + 2 * ns], body[3 + 2 * ns]

@@ -88,6 +88,30 @@ def check_file(jpg, img, w, h, color, cfg):
     return d
 
 
+def q18_applies(jpg, img, w, h, color, cfg):
+    """True iff some DC category the scans emit (predictor reset every `restart_interval` blocks) has no code in the
+    file's DC table of its component: the situation of SURVEY.md Q18 (src/huffman.rs:223-228, 281-285)."""
+    d = t81.decode(jpg, headers_only=True)
+    dc_syms = {th: set(values) for tc, th, counts, values in d.dht if tc == 0}
+    ref = orc.coefficients(img, w, h, CT[color][0], **cfg)
+    ri = cfg["restart_interval"]
+    ncomp = NCOMP[color]
+    table_of = {1: [0], 3: [0, 1, 1]}.get(ncomp, [1, 1, 1, 0] if color == "cmyk" else [0, 1, 1, 0])  # Q12
+    for c in range(ncomp):
+        _, hs, vs, _ = d.components[c]
+        pw = d.mcu_cols * hs
+        tw = -(-(-(-w // 8)) // (d.hmax // hs))
+        th_ = -(-(-(-h // 8)) // (d.vmax // vs))
+        dcs = ref[c].reshape(-1, pw, 64)[:th_, :tw, 0].reshape(-1).astype(np.int64)  # optimized => one scan per component, true grid
+        prev = np.concatenate([[0], dcs[:-1]])
+        prev[::ri] = 0  # encoder.rs:833-839, 895-901: the predictor resets at restart points
+        diff = ((dcs - prev + 32768) % 65536) - 32768  # i16 wrap
+        cats = {int(abs(int(v))).bit_length() for v in diff}
+        if not cats <= dc_syms[table_of[c]]:
+            return True
+    return False
+
+
 CASES = [
     ("rgb", 75, 53, dict(quality=85, sampling=(2, 2))),
     ("rgb", 64, 48, dict(quality=90, sampling=(1, 1))),
@@ -212,9 +236,9 @@ if _HAVE_HYPOTHESIS:
         except (t81.JpegSyntaxError, AssertionError, IndexError):
             # Q18: with optimized tables and restarts a DC category that occurs only at a restart boundary has no code
             # (the histogram never resets the predictor); the reference's release build then writes the value bits
-            # without a code and the stream is knowingly undecodable or decodes to other coefficients. No other
-            # combination may fail. (The fixed CASES above cover optimized + restart inputs that do not hit Q18.)
-            if not (cfg.get("optimize_huffman") and cfg.get("restart_interval")):
+            # without a code and the stream is knowingly undecodable or decodes to other coefficients. Nothing else
+            # may fail, and the Q18 condition is verified, not assumed.
+            if not (cfg.get("optimize_huffman") and cfg.get("restart_interval") and q18_applies(jpg, img, w, h, color, cfg)):
                 raise
 
 
