@@ -184,3 +184,38 @@ def test_optimized_huffman_host_matches_oracle():
         assert rc == 0
         want_len, want_vals = orc.huffman_optimized(f.tolist())
         assert list(length) == want_len and list(values)[:n.value] == want_vals
+
+
+def test_host_entry_points_survive_arbitrary_params():
+    """The planner behind the host-only entry points takes whatever bytes a caller puts into jpgb_params (pointers
+    excepted): it must answer with JPGB_OK / BAD_PARAMS / ZERO_DIMENSIONS consistently, never crash or disagree."""
+    import random
+    from jpeg_encoder_b200.encoder import _CoefLayout, _Params, _Strip
+    lib = je.load_library()
+    rnd = random.Random(4)
+    seen = set()
+    for _ in range(6000):
+        p = _Params()
+        raw = (C.c_uint8 * C.sizeof(p)).from_buffer(p)
+        for i in range(C.sizeof(p)):
+            raw[i] = rnd.getrandbits(8) if rnd.random() < 0.5 else rnd.choice([0, 1, 2, 4, 0x11, 0x22, 0x41, 9, 255])
+        p.n_app, p.apps = 0, None  # pointers must be valid by contract
+        if rnd.random() < 0.7:
+            p.color_type = rnd.randrange(0, 11)
+            p.sampling = rnd.choice([0x11, 0x12, 0x21, 0x22, 0x41, 0x42, 0x14, 0x24, 0x44, 0x33, 0x00, 0x91, 0xA2])
+            p.progressive_scans = rnd.choice([0, 1, 2, 4, 64, 65, 255])
+            p.qtable_kind[0], p.qtable_kind[1] = rnd.randrange(0, 12), rnd.randrange(0, 12)
+        n, ns, lay, k = C.c_size_t(), C.c_uint32(), _CoefLayout(), C.c_uint32()
+        arr = (_Strip * 8)()
+        r1 = lib.jpgb_build_header(C.byref(p), None, 0, C.byref(n))
+        r2 = lib.jpgb_scan_count(C.byref(p), C.byref(ns))
+        r3 = lib.jpgb_coef_layout_for(C.byref(p), C.byref(lay))
+        r4 = lib.jpgb_plan_strips(C.byref(p), 8, arr, C.byref(k))
+        assert r1 == r2 == r3 and r1 in (0, 2, 5)          # one verdict on the settings
+        assert r4 == r1 or (r1 == 0 and r4 == 5)           # strips additionally need a restart interval
+        if r1 == 0:
+            buf = (C.c_uint8 * n.value)()
+            assert lib.jpgb_build_header(C.byref(p), buf, n.value, C.byref(n)) == 0 and bytes(buf[:2]) == b"\xff\xd8"
+            assert 1 <= ns.value <= 4 * 64 and lay.blocks_per_image > 0
+        seen.add(r1)
+    assert seen == {0, 2, 5}
