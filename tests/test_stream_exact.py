@@ -219,7 +219,7 @@ if _HAVE_HYPOTHESIS:
             cfg["qtables"] = (draw(st.integers(0, 8)), draw(st.integers(0, 8)))
         return color, w, h, cfg, draw(st.integers(0, 2 ** 31 - 1)), draw(st.sampled_from(["photo", "noise", "flat"]))
 
-    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=120, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
     @given(_random_case())
     def test_oracle_random_settings_decode_exactly(case):
         color, w, h, cfg, seed, kind = case
