@@ -5,8 +5,11 @@
 
 A step = one pass of the whole encode path (colour -> DCT -> quant -> entropy -> stuffed JFIF bytes)
 over one batch of synthetic frames. Default workload: BASELINE config 3, a batch of 1920x1080 RGB
-frames, q=90, 4:2:0, standard Huffman tables, sharded by image (each rank owns `--batch` frames: weak
-scaling, no data-path collective). `value` is measured with inputs resident in HBM; `e2e` goes
+frames, q=90, 4:2:0, standard Huffman tables: a FIXED batch of 1024 frames sharded by image over the ranks
+(strong scaling, no data-path collective; the weak variant -- 1024 frames on every GPU -- is reported beside it
+under `weak` at N > 1). The same line carries `c5`: BASELINE config 5, one 16384^2 progressive image cut into
+restart-aligned strips, one per GPU, pieces gathered to rank 0 over NVLink -- the only path with a data collective --
+parity-gated against the oracle. `value` is measured with inputs resident in HBM; `e2e` goes
 through the host-buffer C ABI (pinned host pixels in, host JPEG bytes out, copies inside the timed
 region). `roofline` is the colour+DCT+quant kernel against the measured HBM peak. `cpu_baseline`
 is the CPU restatement of the reference (oracle/) on the host cores: a reported baseline, not the
@@ -188,15 +191,25 @@ def run_product(args):
     cfg = resolve_cfg(cfg)
     if args.workload in ("c5", "c5o"):
         return run_strips(args, rank, world, local, dev_t)
-    batch = args.batch or def_batch
     bpp = BPP[color]
     img_bytes = width * height * bpp
-    mp_per_step = batch * width * height / 1e6
+    # BASELINE config 3 is a FIXED batch sharded by image: rank r owns shard_batch(total, world, r) (strong scaling).
+    # `--batch` overrides the total. The weak variant (the whole batch on every GPU) is reported beside it at N > 1.
+    from jpeg_encoder_b200 import sharding
+    total_frames = args.batch or def_batch
+    lo, hi = sharding.shard_batch(total_frames, world, rank)
+    batch = hi - lo
+    if batch == 0:
+        raise SystemExit("bench.py: fewer frames than ranks")
+    weak_batch = total_frames if (world > 1 and args.workload == "c3" and not args.no_weak) else 0
+    resident = max(batch, weak_batch)
 
-    n_distinct = min(DISTINCT, batch)
+    n_distinct = min(DISTINCT, total_frames)
     frames = frames_for(width, height, color, n_distinct)
-    # rank r starts its repeat cycle at a different frame so ranks do not encode identical batches
-    order = [(i + rank) % n_distinct for i in range(batch)]
+    # frame i of the global batch is distinct frame i % n_distinct
+    order_global = [i % n_distinct for i in range(total_frames)]
+    order = order_global[lo:hi]
+    order_weak = [(i + rank) % n_distinct for i in range(weak_batch)]
 
     stream = torch.cuda.current_stream()
     device = je.Device(local, cuda_stream=stream.cuda_stream)
@@ -205,30 +218,57 @@ def run_product(args):
 
     # inputs resident in HBM (image stride padded to 256 B)
     stride = (img_bytes + 255) & ~255
-    d_in = torch.empty(batch * stride, dtype=torch.uint8, device=dev_t)
+    d_in = torch.empty(resident * stride, dtype=torch.uint8, device=dev_t)
     d_distinct = [torch.from_numpy(f.reshape(-1)).to(dev_t) for f in frames]
-    for i, k in enumerate(order):
-        d_in[i * stride:i * stride + img_bytes].copy_(d_distinct[k])
-    torch.cuda.synchronize()
 
-    # parity gate: the bytes this run produces must equal the oracle's (un-timed)
+    def fill(order_):
+        for i, k in enumerate(order_):
+            d_in[i * stride:i * stride + img_bytes].copy_(d_distinct[k])
+        torch.cuda.synchronize()
+
+    fill(order)
+
+    # parity gate (un-timed): EVERY file of the device-resident batch -- the path that is timed below -- must equal
+    # the oracle's bytes; the files are brought back once and compared one by one
+    from cases import oracle_encode
+    want = [oracle_encode(f, width, height, color, cfg) for f in frames]
     d_files, offs = enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
     total = offs[-1]
-    from cases import oracle_encode
+    blob = device.download(d_files, total)
+    for i in range(batch):
+        if blob[offs[i]:offs[i + 1]] != want[order[i]]:
+            raise SystemExit("bench.py: device-batch file %d differs from the oracle -- number would be invalid" % (lo + i))
+    del blob
     check = sorted(set([0, batch // 2, batch - 1]))[:3]
-    outs = enc.encode_batch([frames[order[i]] for i in check], width, height, ct)
-    for i, o in zip(check, outs):
-        want = oracle_encode(frames[order[i]], width, height, color, cfg)
-        if o != want:
-            raise SystemExit("bench.py: GPU bytes differ from the oracle for frame %d -- number would be invalid" % i)
-        if len(o) != offs[i + 1] - offs[i]:
-            raise SystemExit("bench.py: device-batch file size differs from the host-batch one for frame %d" % i)
     out_bytes_per_step = int(total)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_device(n_frames):
+        """K timed steps of the device-resident path over the first n_frames resident frames: (ms per step max over
+        ranks, per-stage ms, launches)."""
+        for _ in range(args.warmup):
+            enc.encode_batch_device(d_in.data_ptr(), stride, n_frames, width, height, ct)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_ms_, launches_ = {}, 0
+        e0.record(stream)
+        for _ in range(args.steps):
+            enc.encode_batch_device(d_in.data_ptr(), stride, n_frames, width, height, ct)
+            launches_ += device.last_launch_count()
+            for k, v in (device.last_timing() or {}).items():
+                stage_ms_[k] = stage_ms_.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t_ = torch.tensor([ms_], device=dev_t)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_ / args.steps, stage_ms_, launches_
 
     # ---- device-resident timing ----
     device.set_timing(True)
@@ -238,21 +278,7 @@ def run_product(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    for _ in range(args.warmup):
-        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {}
-    launches = 0
-    e0.record(stream)
-    for _ in range(args.steps):
-        enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
-        launches += device.last_launch_count()
-        for k, v in (device.last_timing() or {}).items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_per_step, stage_ms, launches = timed_device(batch)
     if rank == 0:
         # the timed region is tens of milliseconds: keep the same work running (un-timed) for about a
         # second so that the 50 ms clock samples are taken under this load
@@ -261,12 +287,16 @@ def run_product(args):
             enc.encode_batch_device(d_in.data_ptr(), stride, batch, width, height, ct)
     clocks = sampler.stop() if rank == 0 else None
     barrier()
-    if world > 1:
-        t = torch.tensor([ms], device=dev_t)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = mp_per_step * world / (ms_per_step / 1e3)
+    mp_per_step = total_frames * width * height / 1e6  # whole job: all ranks' frames
+    value = mp_per_step / (ms_per_step / 1e3)
+
+    weak = None
+    if weak_batch:
+        fill(order_weak)
+        w_ms, _, _ = timed_device(weak_batch)
+        weak = {"frames_per_gpu": weak_batch, "ms_per_step": w_ms, "value": weak_batch * world * width * height / 1e6 / (w_ms / 1e3),
+                "unit": "megapixels/s", "note": "every GPU encodes its own %d frames (per-GPU work fixed as N grows)" % weak_batch}
+        fill(order)
 
     # ---- end to end through the host-buffer C ABI (pinned pixels in, host bytes out) ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -302,7 +332,7 @@ def run_product(args):
         t = torch.tensor([e2e_s], device=dev_t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = mp_per_step * world * e2e_steps / e2e_s
+    e2e_value = mp_per_step * e2e_steps / e2e_s
 
     # what the link alone can do: the same pinned frames copied to the device back to back, nothing else running
     # (explains the end-to-end number: it moves bpp bytes per pixel over PCIe)
@@ -321,6 +351,37 @@ def run_product(args):
     torch.cuda.synchronize()
     h2d_gbs = n_copy * img_bytes / (time.perf_counter() - t0) / 1e9
     del stage_d
+
+    # the crate's own call shape: Encoder::encode(&[u8]) -> one image per call, PAGEABLE input (a plain Vec<u8>),
+    # bytes handed to the sink. Measured beside the pinned batch figure (rank 0 reports its own rate).
+    def drop_in_rate(src_frames, n_calls):
+        enc.encode(src_frames[0], width, height, ct)
+        t0_ = time.perf_counter()
+        for i in range(n_calls):
+            enc.encode(src_frames[i % len(src_frames)], width, height, ct)
+        return n_calls * width * height / 1e6 / (time.perf_counter() - t0_)
+
+    n_calls = 24 if img_bytes < 64e6 else 3
+    drop_pageable = drop_in_rate(frames, n_calls)
+    drop_pinned = drop_in_rate([t_.numpy() for t_ in pinned], n_calls)
+    if enc.encode(frames[0], width, height, ct) != want[0]:
+        raise SystemExit("bench.py: jpgb_encode bytes differ from the oracle")
+
+    # ---- BASELINE config 5 inside the default line: one 16384^2 progressive image cut into restart-aligned strips,
+    # one strip per GPU, pieces gathered to rank 0 (the only path with a data collective), parity-gated ----
+    c5 = None
+    if args.workload == "c3" and not args.no_c5:
+        del d_in, d_distinct
+        device.close()
+        torch.cuda.empty_cache()
+        c5_args = argparse.Namespace(**vars(args))
+        c5_args.workload, c5_args.size, c5_args.skip_parity = "c5", args.c5_size, False
+        c5_args.steps, c5_args.warmup = max(3, min(args.steps, 10)), max(3, min(args.warmup, 5))
+        c5_line = run_strips(c5_args, rank, world, local, dev_t, extra=True)
+        if rank == 0:
+            c5 = {k: c5_line[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "gpu_launches", "stage_ms_per_step", "gather_ms_per_step")}
+            c5.update(parity=True, workload=c5_line["config"]["workload"], strips=c5_line["config"]["strips"], bytes_out=c5_line["config"]["bytes_out"],
+                      collective=c5_line["config"]["collective"], e2e=c5_line["e2e"], stage_a_frac_of_hbm_peak=c5_line["roofline"]["frac"])
 
     if rank != 0:
         if world > 1:
@@ -366,31 +427,40 @@ def run_product(args):
     line = {
         "metric": "megapixels/sec encoded, byte-identical to the reference restatement",
         "value": value, "unit": "megapixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8 in / i32 arithmetic / i16 coefficients", "data": "synthetic",
-        "config": {"workload": desc, "workload_id": args.workload, "frames_per_gpu": batch, "width": width, "height": height,
+        "config": {"workload": desc, "workload_id": args.workload, "frames_total": total_frames, "frames_per_gpu": batch,
+                   "sharding": "fixed batch of %d frames, rank r encodes frames shard_batch(total, N, r): no data-path collective" % total_frames,
+                   "width": width, "height": height,
                    "settings": {k: (v if k != "qtables" else "custom u16[64] x2") for k, v in cfg.items()},
                    "distinct_frames": n_distinct, "bytes_out_per_step_per_gpu": out_bytes_per_step,
                    "l2": "inputs (%.1f MB per step per GPU) larger than L2, no flush" % (batch * img_bytes / 1e6)
                    if batch * img_bytes > 200e6 else "inputs smaller than L2 (%.1f MB): single-image latency case" % (batch * img_bytes / 1e6)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": batch * img_bytes * world,
+        "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": total_frames * img_bytes,
                 "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "api": "jpgb_encode_batch_pinned (pinned host pixels -> host JPEG files; chunked upload/encode/download overlap)",
                 "h2d_link_gbs_measured": h2d_gbs, "h2d_gbs_in_e2e": batch * img_bytes * e2e_steps / e2e_s / 1e9,
                 "frac_of_link": (batch * img_bytes * e2e_steps / e2e_s / 1e9) / h2d_gbs,
-                "note": "end to end is bound by the host->device link (bpp bytes per pixel over PCIe): frac_of_link = h2d_gbs_in_e2e / h2d_link_gbs_measured (rank 0)"},
+                "note": "end to end is bound by the host->device link (bpp bytes per pixel over PCIe): frac_of_link = h2d_gbs_in_e2e / h2d_link_gbs_measured (rank 0)",
+                "drop_in_call": {"api": "jpgb_encode: one image per call, as Encoder::encode(&[u8]) binds it", "calls": n_calls, "unit": "megapixels/s",
+                                 "pageable_input": drop_pageable, "pinned_input": drop_pinned,
+                                 "note": "rank 0's own rate; pageable input is staged through the context's two pinned buffers"}},
         "gpu_launches": launches,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if weak:
+        line["weak"] = weak
+    if c5:
+        line["c5"] = c5
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ---- one very large image, strips across the GPUs (BASELINE config 5) ---------------------------
-def run_strips(args, rank, world, local, dev_t):
+def run_strips(args, rank, world, local, dev_t, extra=False):
     import torch
     import torch.distributed as dist
     import images
@@ -428,15 +498,23 @@ def run_strips(args, rank, world, local, dev_t):
     def encode_once():
         return encode_strip(d_strip.data_ptr())
 
-    def step(gather=True):
+    gather_events = []
+
+    def step(gather=True, timed=False):
         d_bytes, offs = encode_once()
         launches = device.last_launch_count()
         tm = device.last_timing()
         out = None
         if world > 1 and gather:
-            # wrap the context-owned device buffer (no copy) and gather the pieces to rank 0 over NCCL
+            # wrap the context-owned device buffer (no copy) and gather the pieces to rank 0 over NVLink
             local_bytes = _as_tensor(d_bytes, offs[-1], dev_t)
+            if timed:
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
             out = sharding.gather_strip_pieces(local_bytes, offs, rank, world, dev_t)
+            if timed:
+                g1.record(stream)
+                gather_events.append((g0, g1))
         elif gather:
             out = _as_tensor(d_bytes, offs[-1], dev_t)
         return out, launches, tm
@@ -461,7 +539,7 @@ def run_strips(args, rank, world, local, dev_t):
 
     device.set_timing(True)
     sampler = ClockSampler(local)  # started before the warm-up, see run_batch
-    if rank == 0:
+    if rank == 0 and not extra:
         sampler.start()
         time.sleep(0.3)
     for _ in range(args.warmup):
@@ -471,7 +549,7 @@ def run_strips(args, rank, world, local, dev_t):
     stage_ms, launches = {}, 0
     e0.record(stream)
     for _ in range(args.steps):
-        _, l, tm = step()
+        _, l, tm = step(timed=True)
         launches += l
         for k, v in (tm or {}).items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
@@ -483,12 +561,18 @@ def run_strips(args, rank, world, local, dev_t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_events) / args.steps if gather_events else 0.0
+    if world > 1:  # the slowest rank's gather (rank 0 receives, the others send)
+        t = torch.tensor([gather_ms], device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t.item())
     # keep the same work running (un-timed, same count on every rank) for about a second so that the
     # 50 ms clock samples are taken under this load
-    for _ in range(int(min(400, 1000.0 / max(ms_per_step, 1.0)))):
-        step()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    if not extra:
+        for _ in range(int(min(400, 1000.0 / max(ms_per_step, 1.0)))):
+            step()
+        barrier()
+    clocks = sampler.stop() if (rank == 0 and not extra) else None
     mp = width * height / 1e6
     value = mp / (ms_per_step / 1e3)
 
@@ -515,9 +599,9 @@ def run_strips(args, rank, world, local, dev_t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     if rank != 0:
-        if world > 1:
+        if world > 1 and not extra:
             dist.destroy_process_group()
-        return
+        return None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = (float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if os.path.exists(peaks_path) \
         else (6650.0, "fallback (B200_PROFILING.md)")
@@ -541,11 +625,14 @@ def run_strips(args, rank, world, local, dev_t):
                 "api": "pinned host strip -> jpgb_encode_strip_device -> NCCL gather -> host file on rank 0"},
         "gpu_launches": launches,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-        "roofline": {"bound": "hbm", "kernel": "stage_a_fast_kernel (colour+decimate+fDCT+quant), rank 0's strip", "achieved": achieved,
+        "gather_ms_per_step": gather_ms,
+        "roofline": {"bound": "hbm", "kernel": "stage_a_warp_kernel (colour+decimate+fDCT+quant), rank 0's strip", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes, "ms_per_launch": a_ms},
         "cpu_baseline": None,
     }
+    if extra:
+        return line
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -614,6 +701,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--size", type=int, default=0, help="c5 only: square image size override (testing)")
+    ap.add_argument("--c5-size", type=int, default=0, help="size override of the config-5 leg inside the default line (testing)")
+    ap.add_argument("--no-c5", action="store_true", help="default workload only: skip the config-5 (strips + gather) leg")
+    ap.add_argument("--no-weak", action="store_true", help="default workload only: skip the weak-scaling leg at N > 1")
     ap.add_argument("--skip-parity", action="store_true", help="c5 only: skip the whole-image oracle comparison")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -95,7 +95,9 @@ int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, 
 void jpgb_free(void *buf);
 
 /* Same, delivering the bytes through a JfifWrite::write_all-style callback
- * (src/writer.rs:76-82). A non-zero return from `write_all` aborts with JPGB_ERR_SINK. */
+ * (src/writer.rs:76-82). A non-zero return from `write_all` aborts with JPGB_ERR_SINK. The callback is
+ * invoked once, on the context's pinned download buffer (no intermediate copy). `pixels` may be pageable
+ * (it is staged through pinned buffers of the context) or pinned / registered (copied directly). */
 typedef int (*jpgb_write_all_fn)(void *user, const uint8_t *buf, size_t len);
 int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len,
                         jpgb_write_all_fn write_all, void *user);
@@ -106,6 +108,9 @@ int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *
  * JPGB_YCCK (4). planes[c] holds width*height samples of component c, taken verbatim. */
 int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len,
                        uint8_t **out, size_t *out_len);
+/* Same, delivering the bytes to a JfifWrite::write_all-style callback (what `Encoder<W>::encode_image` binds). */
+int jpgb_encode_planar_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len,
+                               jpgb_write_all_fn write_all, void *user);
 
 /* Batch of `n` images of identical geometry and settings (BASELINE config 3; no reference
  * equivalent -- the crate is called once per image). Host memory in and out.

@@ -74,7 +74,9 @@ struct jpgb_encoder {
         scan_tmp, hist, piece_off, out2, pixels2, status, scan_err;
     std::vector<uint8_t> last_plan, last_tables; // what the device currently holds
     double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
-    PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out;
+    PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out, h_stage[2];
+    cudaEvent_t ev_stage[2] = {};
+    bool stage_busy[2] = {};
     int out_slot = 0; // which of out / out2 the next encode_device writes
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_enc[2] = {};
@@ -369,6 +371,35 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     return JPGB_OK;
 }
 
+// Host -> device copy of caller memory. Pinned (or registered) memory goes straight to the copy engine. Pageable
+// memory -- what `Encoder::encode(&[u8])` hands over -- is staged through two pinned buffers owned by the context:
+// while the copy engine drains one, the host fills the other, so the DMA never waits for a page-locked bounce
+// inside the driver and the copy stays asynchronous.
+constexpr size_t kStageBytes = 8u << 20;
+cudaError_t upload_host(jpgb_encoder *enc, void *d_dst, const uint8_t *src, size_t bytes, cudaStream_t s) {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError(); // an unregistered pointer may leave a sticky-free error code behind on older runtimes
+    if (pinned || bytes <= 65536) return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, s);
+    for (size_t off = 0, k = 0; off < bytes; off += kStageBytes, ++k) {
+        const int b = (int)(k & 1);
+        const size_t n = std::min(kStageBytes, bytes - off);
+        cudaError_t e = enc->h_stage[b].reserve(kStageBytes);
+        if (e != cudaSuccess) return e;
+        if (enc->stage_busy[b]) { // the DMA that last read this buffer must be done before the host overwrites it
+            e = cudaEventSynchronize(enc->ev_stage[b]);
+            if (e != cudaSuccess) return e;
+        }
+        std::memcpy(enc->h_stage[b].p, src + off, n);
+        e = cudaMemcpyAsync(static_cast<uint8_t *>(d_dst) + off, enc->h_stage[b].p, n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(enc->ev_stage[b], s);
+        if (e != cudaSuccess) return e;
+        enc->stage_busy[b] = true;
+    }
+    return cudaSuccess;
+}
+
 // Host pixels -> host files for n images, pipelined in chunks over three streams: while chunk c is
 // encoded on the context's stream, chunk c+1 is uploaded (s_h2d) and the files of chunk c-1 are
 // downloaded (s_d2h) into one pinned buffer owned by the context. PCIe moves 3 B/pixel in and the
@@ -396,7 +427,7 @@ int encode_host_pipelined(jpgb_encoder *enc, const Plan &plan, const uint8_t *co
             if (e != cudaSuccess) return e;
         }
         for (uint32_t i = lo; i < hi; ++i) {
-            cudaError_t e = cudaMemcpyAsync(px.as<uint8_t>() + stride * (i - lo), pixels[i], img_bytes, cudaMemcpyHostToDevice, enc->s_h2d);
+            cudaError_t e = upload_host(enc, px.as<uint8_t>() + stride * (i - lo), pixels[i], img_bytes, enc->s_h2d);
             if (e != cudaSuccess) return e;
         }
         return cudaEventRecord(enc->ev_in[c & 1], enc->s_h2d);
@@ -521,6 +552,7 @@ int jpgb_encoder_create(int device, void *cuda_stream, jpgb_encoder **out) {
         cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_enc[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming);
     }
     *out = e;
     return JPGB_OK;
@@ -544,6 +576,8 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
         if (e->ev_enc[i]) cudaEventDestroy(e->ev_enc[i]);
+        if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
+        e->h_stage[i].release();
     }
     for (int i = 0; i < JPGB_N_STAGES; ++i)
         for (int k = 0; k < 2; ++k)
@@ -564,12 +598,9 @@ int jpgb_encode(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, 
 
 void jpgb_free(void *buf) { std::free(buf); }
 
-int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len, uint8_t **out,
-                       size_t *out_len) {
-    if (!enc) return JPGB_ERR_BAD_PARAMS;
-    if (!p || !planes || !out || !out_len) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
-    *out = nullptr;
-    *out_len = 0;
+// Encoder::encode_image's planes -> the file in the context's pinned output buffer (enc->h_out)
+static int encode_planar_pinned(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len, size_t *out_len) {
+    if (!p || !planes) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
     const uint8_t ct = p->color_type;
     if (ct != JPGB_LUMA && ct != JPGB_YCBCR && ct != JPGB_CMYK && ct != JPGB_YCCK)
         return fail(enc, JPGB_ERR_BAD_PARAMS, "planar input takes a JPEG colour type: Luma, Ycbcr, Cmyk or Ycck");
@@ -585,31 +616,60 @@ int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *c
     CK(enc->pixels.reserve(stride), "alloc planes");
     for (int c = 0; c < plan.ncomp; ++c) {
         if (!planes[c]) return fail(enc, JPGB_ERR_BAD_PARAMS, "null plane");
-        CK(cudaMemcpyAsync(enc->pixels.as<uint8_t>() + plane_bytes * c, planes[c], plane_bytes, cudaMemcpyHostToDevice, enc->stream), "upload plane");
+        CK(upload_host(enc, enc->pixels.as<uint8_t>() + plane_bytes * c, planes[c], plane_bytes, enc->stream), "upload plane");
     }
     std::vector<uint64_t> off;
     const int rc2 = encode_device(enc, plan, enc->pixels.as<uint8_t>(), stride, 1, off);
     if (rc2 != JPGB_OK) return rc2;
     const size_t sz = (size_t)off[1];
-    *out = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
-    if (!*out) return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
-    CK(cudaMemcpyAsync(*out, enc->out.p, sz, cudaMemcpyDeviceToHost, enc->stream), "download file");
+    CK(enc->h_out.reserve(sz ? sz : 1), "alloc pinned output");
+    CK(cudaMemcpyAsync(enc->h_out.p, enc->out.p, sz, cudaMemcpyDeviceToHost, enc->stream), "download file");
     CK(cudaStreamSynchronize(enc->stream), "download sync");
     *out_len = sz;
     timing_end(enc);
     return JPGB_OK;
 }
 
+int jpgb_encode_planar(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len, uint8_t **out,
+                       size_t *out_len) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!out || !out_len) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    *out = nullptr;
+    *out_len = 0;
+    size_t sz = 0;
+    const int rc = encode_planar_pinned(enc, p, planes, plane_len, &sz);
+    if (rc != JPGB_OK) return rc;
+    *out = static_cast<uint8_t *>(std::malloc(sz ? sz : 1));
+    if (!*out) return fail(enc, JPGB_ERR_NOMEM, "out of host memory");
+    std::memcpy(*out, enc->h_out.p, sz);
+    *out_len = sz;
+    return JPGB_OK;
+}
+
+int jpgb_encode_planar_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *const planes[4], size_t plane_len,
+                               jpgb_write_all_fn write_all, void *user) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!write_all) return fail(enc, JPGB_ERR_BAD_PARAMS, "null sink");
+    size_t sz = 0;
+    const int rc = encode_planar_pinned(enc, p, planes, plane_len, &sz);
+    if (rc != JPGB_OK) return rc;
+    if (write_all(user, enc->h_out.as<uint8_t>(), sz) != 0) return fail(enc, JPGB_ERR_SINK, "sink write_all failed");
+    return JPGB_OK;
+}
+
+// The sink receives the file straight from the context's pinned download buffer: one write_all call, no
+// intermediate copy (the reference makes many small write_all calls, src/writer.rs:123-202; only the number of
+// calls differs, the bytes and the error propagation do not).
 int jpgb_encode_to_sink(jpgb_encoder *enc, const jpgb_params *p, const uint8_t *pixels, size_t len, jpgb_write_all_fn write_all,
                         void *user) {
-    if (!write_all) return JPGB_ERR_BAD_PARAMS;
-    uint8_t *buf = nullptr;
-    size_t n = 0;
-    const int rc = jpgb_encode(enc, p, pixels, len, &buf, &n);
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!write_all) return fail(enc, JPGB_ERR_BAD_PARAMS, "null sink");
+    const uint8_t *px[1] = {pixels};
+    const uint8_t *files = nullptr;
+    uint64_t offs[2] = {0, 0};
+    const int rc = encode_host_batch(enc, p, px, len, 1, nullptr, nullptr, &files, offs);
     if (rc != JPGB_OK) return rc;
-    const int wrc = write_all(user, buf, n);
-    std::free(buf);
-    if (wrc != 0) return fail(enc, JPGB_ERR_SINK, "sink write_all failed");
+    if (write_all(user, files + offs[0], (size_t)(offs[1] - offs[0])) != 0) return fail(enc, JPGB_ERR_SINK, "sink write_all failed");
     return JPGB_OK;
 }
 

@@ -7,18 +7,21 @@
 //   fdct (jfdctint islow, i32, x8 scaled)                src/fdct.rs:107-238
 //   Operations::quantize_block (reciprocal, zig-zag)     src/encoder.rs:1265-1271, quantization.rs:291-307
 //
-// Work decomposition: a CTA owns a tile of `groups` x 32 MCUs of one MCU row. The tile's pixel rows
-// are staged into shared memory with 128-bit coalesced loads (edge pixels replicated while staging,
-// so every later read is in-bounds). A *warp task* is 32 blocks with the same (component, v, h)
-// position in 32 consecutive MCUs: each lane owns one whole 8x8 block in registers, so both DCT
-// passes, the transpose between them and the zig-zag permutation are register renaming -- no
-// shuffles, no shared-memory round trip, no divergence. Each lane then writes its 128-byte block.
+// Work decomposition (stage_a_warp_kernel, the path of every BASELINE configuration): persistent and
+// warp-autonomous. Each warp owns a private shared-memory tile of 32 full-resolution blocks (256 pixels) x one or
+// more MCU rows, fetched by TMA (cp.async near image edges, which are replicated while staging), and walks warp
+// tiles on its own -- no CTA barrier. A *warp task* is 32 consecutive blocks of one component block row: each
+// lane owns one whole 8x8 block in registers, so both DCT passes, the transpose between them and the zig-zag
+// permutation are register renaming -- no shuffles, no shared-memory round trip, no divergence. Each lane then
+// writes its 128-byte block with 256-bit stores. stage_a_kernel<CT> is the generic CTA-tile variant for what the
+// warp kernel does not instantiate.
 //
 // All arithmetic is 32-bit integer; tensor cores are not used (the DCT must be bit-exact).
 #include <cuda.h>
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <utility>
 
 #include "kernels.h"
@@ -651,6 +654,12 @@ inline bool make_pixel_tensor_map(CUtensorMap &map, const StageAParams &p, int b
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+constexpr int kMaxDevices = 64;
+struct LaunchInfo {
+    bool ready = false;
+    int dev = -1, n_sms = 0, ctas_per_sm = 0;
+};
+
 template <int CT, int HS, int VS>
 cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     constexpr int BPP = Fmt<CT>::BPP;
@@ -658,19 +667,29 @@ cudaError_t launch_warp_variant(const StageAParams &p, cudaStream_t stream) {
     constexpr int TILE = 256 * BPP * 8 * VS * MR;
     const size_t smem = (size_t)4 * TILE + 4 * sizeof(uint64_t); // 4 warps per CTA: one private tile and one mbarrier each
     auto kernel = stage_a_warp_kernel<CT, HS, VS>;
-    // per device, once: opt in to the dynamic shared memory and ask how many CTAs fit on an SM
-    static int cached_dev = -1, n_sms = 0, ctas_per_sm = 0;
+    // per device, once: opt in to the dynamic shared memory and ask how many CTAs fit on an SM. Contexts on
+    // several host threads (and several devices) launch concurrently: the cache is per device and guarded.
+    static std::mutex mu;
+    static LaunchInfo cache[kMaxDevices];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev != cached_dev) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 128, smem);
-        if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        cached_dev = dev;
+    LaunchInfo info;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        LaunchInfo &c = cache[dev < kMaxDevices ? dev : kMaxDevices - 1];
+        if (!c.ready || c.dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.ctas_per_sm, kernel, 128, smem);
+            if (e != cudaSuccess) return e;
+            if (c.ctas_per_sm < 1) c.ctas_per_sm = 1;
+            c.dev = dev;
+            c.ready = true;
+        }
+        info = c;
     }
+    const int n_sms = info.n_sms, ctas_per_sm = info.ctas_per_sm;
     constexpr int MCUS = 32 / HS;
     const unsigned long long n_tiles = (unsigned long long)((p.mcu_cols + MCUS - 1) / MCUS) * ((p.mcu_rows + MR - 1) / MR) * p.n_images;
     unsigned long long grid = (unsigned long long)n_sms * ctas_per_sm;

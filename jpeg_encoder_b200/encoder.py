@@ -186,6 +186,7 @@ def load_library():
     l.jpgb_encode_batch.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.c_uint32,
                                     C.POINTER(u8p), C.POINTER(C.c_size_t)]
     l.jpgb_encode_planar.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.POINTER(u8p), C.POINTER(C.c_size_t)]
+    l.jpgb_encode_planar_to_sink.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, vp, vp]
     l.jpgb_encode_batch_pinned.argtypes = [vp, C.POINTER(_Params), C.POINTER(vp), C.c_size_t, C.c_uint32,
                                            C.POINTER(vp), C.POINTER(C.c_uint64)]
     l.jpgb_encode_batch_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32,

@@ -274,6 +274,86 @@ def test_config5_progressive_420_medium():
           img=images.photo_like(2048, 2048, 3, seed=6))
 
 
+# ---- BASELINE.json configurations 3, 4 and 5 at FULL size ------------------------------------------
+def _bench_custom_table():
+    import bench
+    return bench.custom_table()
+
+
+def _torch_frame(w, h, ch, seed):
+    """images.synth_frame evaluated on the GPU (seconds instead of minutes at 8192^2 and above), as a host array."""
+    import torch
+    rows = max(1, (1 << 27) // (w * ch))  # bounded temporaries: ~128 MB of output per slab (int64 intermediates are 8x)
+    parts = [images.synth_frame_torch(w, h, ch, seed=seed, row0=r, rows=min(rows, h - r), device="cuda").cpu() for r in range(0, h, rows)]
+    torch.cuda.empty_cache()
+    return torch.cat(parts).numpy()
+
+
+def test_config3_device_batch_every_file():
+    """jpgb_encode_batch_device (the timed path of bench.py): every file of a 96-frame batch, byte for byte."""
+    import torch
+    import jpeg_encoder_b200 as je
+    w, h, n, distinct = 1920, 1080, 96, 6
+    cfg = dict(quality=90, sampling=(2, 2))
+    frames = [images.synth_frame(w, h, 3, seed=s) for s in range(distinct)]
+    want = [oracle_encode(f, w, h, "rgb", cfg) for f in frames]
+    stride = (w * h * 3 + 255) & ~255
+    d_in = torch.zeros(n * stride, dtype=torch.uint8, device="cuda")
+    order = [(i * 5 + i // 7) % distinct for i in range(n)]
+    for i, k in enumerate(order):
+        d_in[i * stride:i * stride + w * h * 3].copy_(torch.from_numpy(frames[k].reshape(-1)))
+    torch.cuda.synchronize()
+    dev = je.default_device(0)
+    enc = make_encoder(cfg, dev)
+    for _ in range(2):  # the second call runs with learnt buffer sizes and cached plan / tables
+        d_files, offs = enc.encode_batch_device(d_in.data_ptr(), stride, n, w, h, je.ColorType.Rgb)
+        blob = dev.download(d_files, offs[-1])
+        assert offs[0] == 0
+        bad = [i for i in range(n) if bytes(blob[offs[i]:offs[i + 1]]) != want[order[i]]]
+        assert not bad, "files differ: %r" % bad[:10]
+
+
+def test_config4a_full_size_gray_custom_tables():
+    t = _bench_custom_table()
+    img = _torch_frame(8192, 8192, 1, seed=3)
+    _same("luma", 8192, 8192, dict(quality=95, sampling=(1, 1), qtables=(t, t)), img=img)
+
+
+def test_config4b_full_size_cmyk_as_ycck_custom_tables():
+    t = _bench_custom_table()
+    img = _torch_frame(8192, 8192, 4, seed=4)
+    _same("cmyk_as_ycck", 8192, 8192, dict(quality=95, sampling=(1, 1), qtables=(t, t)), img=img)
+
+
+def test_config4_tables_above_255_parity_only():
+    """Q10: table entries > 255 are truncated in the DQT segment but quantize with their full value; such files
+    do not decode correctly, so this case is compared on bytes only."""
+    rng = np.random.default_rng(44)
+    t = [int(v) for v in rng.integers(1, 1200, 64)]
+    for color, w, h in (("luma", 2048, 2048), ("cmyk_as_ycck", 2048, 1024)):
+        _same(color, w, h, dict(quality=95, sampling=(1, 1), qtables=(t, t)), img=_torch_frame(w, h, BPP[color], seed=5))
+
+
+def test_config5_full_size_progressive_8_strips_one_gpu():
+    """16384 x 16384 RGB progressive 4:2:0, restart interval 2048, cut into 8 restart-aligned strips that are
+    encoded one after the other on this GPU and concatenated scan-major: equal to the whole-image oracle file."""
+    w = h = 16384
+    cfg = dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048)
+    img = _torch_frame(w, h, 3, seed=7)
+    got, n = _encode_by_strips(img, w, h, "rgb", cfg, 8)
+    assert n == 8
+    want = oracle_encode(img, w, h, "rgb", cfg)
+    assert len(got) == len(want) and got == want
+
+
+def test_config5_full_size_whole_image_one_call():
+    """The same image through the ordinary Encoder::encode call (no strips): 805 MB of pixels, 12 scans."""
+    w = h = 16384
+    cfg = dict(quality=90, sampling=(2, 2), progressive_scans=4, restart_interval=2048)
+    img = _torch_frame(w, h, 3, seed=7)
+    _same("rgb", w, h, cfg, img=img)
+
+
 # ---- one image cut into restart-aligned strips (BASELINE config 5 mechanics, on one GPU) ---------
 def _encode_by_strips(img, w, h, color, cfg, max_strips):
     import torch
