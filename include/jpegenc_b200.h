@@ -184,15 +184,21 @@ int jpgb_download(jpgb_encoder *enc, const void *d_src, size_t n, void *host_dst
 
 /* ---- stage-level entry points (parity tests and roofline timing) ------------------------------ */
 
-/* Block-grid geometry of the coefficient buffer for `p`: per component the MCU-padded grid
- * (blocks_w x blocks_h, raster order, 64 i16 zig-zag coefficients each; Q9, Q14) and the block
- * offset of the component inside one image's buffer. Returns the number of components. */
+/* Layout of the coefficient buffer for `p` (64 i16 zig-zag coefficients per block; Q9). The buffer is ordered the
+ * way the scans of the mode read it (Q14):
+ *  - mcu_order = 1 (interleaved scan, src/encoder.rs:747-791): the blocks of the MCU-padded grids in coding order,
+ *    block of (MCU m in raster order, slot s) = m * blocks_per_mcu + s, slot = slot_base[c] + v * comp_h[c] + h;
+ *  - mcu_order = 0 (sequential / progressive, src/encoder.rs:1012-1031): per component the raster of its TRUE grid
+ *    (true_w x true_h, the one encode_blocks walks), first block at block_offset[c]; blocks that exist only as MCU
+ *    padding are never coded in these modes and are not stored. */
 typedef struct jpgb_coef_layout {
     uint32_t n_components;
     uint32_t blocks_w[4], blocks_h[4]; /* padded grid = mcu_cols*H_c x mcu_rows*V_c */
     uint32_t true_w[4], true_h[4];     /* grid encode_blocks walks (src/encoder.rs:1012-1025) */
-    uint64_t block_offset[4];          /* first block of the component, in blocks */
+    uint64_t block_offset[4];          /* mcu_order = 0: first block of the component, in blocks */
     uint64_t blocks_per_image;
+    uint32_t mcu_order, mcu_cols, mcu_rows, blocks_per_mcu;
+    uint32_t slot_base[4], comp_h[4], comp_v[4];
 } jpgb_coef_layout;
 int jpgb_coef_layout_for(const jpgb_params *p, jpgb_coef_layout *layout);
 
@@ -205,7 +211,8 @@ int jpgb_stage_a_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_p
 /* Per-stage device time of the last jpgb_encode* call on this context, in milliseconds, measured
  * with CUDA events on the context's stream (enabled with jpgb_encoder_set_timing).
  * stage index: 0 = colour+DCT+quant kernel, 1 = histogram + table build (optimized only),
- * 2 = symbol sizing + prefix sums, 3 = bit emission, 4 = byte stuffing + scatter, 5 = H2D, 6 = D2H. */
+ * 2 = entropy coding into chunks + prefix sums, 3 = chunk placement (bit-granular copy into the stream),
+ * 4 = byte stuffing + scatter, 5 = H2D, 6 = D2H. */
 #define JPGB_N_STAGES 7
 void jpgb_encoder_set_timing(jpgb_encoder *enc, int enabled);
 int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]);

@@ -70,10 +70,11 @@ struct jpgb_encoder {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    DevBuf pixels, coef, plan, huff, hdr, hdr_len, nbits, slots, bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos, out, file_off,
-        scan_tmp, hist, piece_off, out2, pixels2, status, scan_err;
+    DevBuf pixels, coef, plan, huff, hdr, hdr_len, scratch, pool, chunk_bits, chunk_pool, chunk_bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos,
+        out, file_off, scan_tmp, hist, piece_off, out2, pixels2, status, scan_err;
     std::vector<uint8_t> last_plan, last_tables; // what the device currently holds
     double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
+    double pool_ratio = 0; // the same for the chunk pool (code bytes incl. per-chunk alignment)
     PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out, h_stage[2];
     cudaEvent_t ev_stage[2] = {};
     bool stage_busy[2] = {};
@@ -200,7 +201,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
             CK(enc->hist.reserve(hist_words * 4), "alloc histogram");
             CK(cudaMemsetAsync(enc->hist.p, 0, hist_words * 4, st), "clear histogram");
             CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
-            enc->launches += n;
+            enc->launches += 1;
             CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_words * 4, cudaMemcpyDeviceToHost, st), "download histogram");
             CK(cudaStreamSynchronize(st), "histogram sync");
         }
@@ -249,67 +250,67 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         }
     }
 
-    // ---- symbol sizing and the two prefix sums ----
-    CK(enc->nbits.reserve(n_visits * 4), "alloc nbits");
-    CK(enc->slots.reserve((n_visits + kSlotTile - 1) / kSlotTile * kSlotTile * 4 * kSlotWords), "alloc code slots");
-    CK(enc->bitpos.reserve((n_visits + 1) * 8), "alloc bitpos");
+    // ---- entropy coding: chunks -> pool, two small prefix sums, placement, stuffing. No host round trip: the pool,
+    // the unstuffed stream and the output are sized from what this context has seen before (first call: a fraction
+    // of the raw pixels); the kernels read the real sizes on the device and raise a flag instead of overrunning, in
+    // which case the affected part of the pipeline is repeated once with exact sizes.
+    const uint64_t n_chunks = (uint64_t)plan.chunks_per_image * n;
+    CK(enc->chunk_bits.reserve(n_chunks * 4), "alloc chunk sizes");
+    CK(enc->chunk_pool.reserve(n_chunks * 4), "alloc chunk places");
+    CK(enc->chunk_bitpos.reserve((n_chunks + 1) * 8), "alloc chunk positions");
     CK(enc->seglen.reserve(n_segs * 4), "alloc seglen");
     CK(enc->segpos.reserve((n_segs + 1) * 8), "alloc segpos");
-    CK(enc->scan_tmp.reserve(scan_tmp_bytes(n_visits > n_segs ? n_visits : n_segs)), "alloc scan scratch");
+    CoderLaunch coder{};
+    CK(coder_launch_config(hp, n, coder), "coder configuration");
+    CK(enc->scratch.reserve(coder.scratch_bytes), "alloc coder scratch");
 
     EntropyBuffers b{};
     b.plan = enc->plan.as<DevPlan>();
     b.coef = enc->coef.as<int16_t>();
     b.huff = enc->huff.as<uint32_t>();
     b.huff_per_image = optimized ? 1 : 0;
-    b.nbits = enc->nbits.as<uint32_t>();
-    b.slots = enc->slots.as<uint32_t>();
-    b.bitpos = enc->bitpos.as<unsigned long long>();
+    b.scratch = enc->scratch.as<uint32_t>();
+    b.chunk_bits = enc->chunk_bits.as<uint32_t>();
+    b.chunk_pool = enc->chunk_pool.as<uint32_t>();
+    b.chunk_bitpos = enc->chunk_bitpos.as<unsigned long long>();
     b.seglen = enc->seglen.as<uint32_t>();
     b.segpos = enc->segpos.as<unsigned long long>();
     b.hdr_len = enc->hdr_len.as<uint32_t>();
     b.hdr = enc->hdr.as<uint8_t>();
     b.hdr_stride = (uint32_t)hdr_stride;
-    b.scan_tmp = enc->scan_tmp.p;
 
-    CK(enc->status.reserve(64), "alloc status");
+    CK(enc->status.reserve(kStatusWords * 8), "alloc status");
     CK(enc->scan_err.reserve(8), "alloc scan flag");
     CK(cudaMemsetAsync(enc->scan_err.p, 0, 8, st), "clear scan flag");
     unsigned long long *scan_err = enc->scan_err.as<unsigned long long>();
-    {
-        StageTimer t(enc, 2);
-        CK(launch_symbol_sizes(b, hp, n, st), "symbol size launch");
-        CK(launch_exclusive_scan(b.nbits, b.bitpos, n_visits, b.scan_tmp, st, &enc->launches, scan_err), "bit position scan");
-        CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
-        CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches, scan_err), "segment position scan");
-        enc->launches += 2;
-    }
 
-    // ---- bit emission, stuffing, scatter: no host round trip. The unstuffed stream and the output are
-    // sized from what this context has seen before (first call: a fraction of the raw pixels); the kernels
-    // read the real sizes on the device and raise a flag instead of overrunning, in which case the tail of
-    // the pipeline is repeated once with exact sizes.
     const uint64_t raw_bytes = (uint64_t)plan.p.width * plan.p.height * plan.bpp * n;
     // learnt bytes per raw byte from earlier calls on this context, else a third of the raw size
     uint64_t ucap = enc->ucap_ratio > 0 ? (uint64_t)(raw_bytes * enc->ucap_ratio) + (uint64_t)n * 4096 + 65536
                                         : raw_bytes / 3 + (uint64_t)n * 4096 + 65536;
     uint64_t ocap = ucap + ucap / 32 + 4096;
-    uint64_t ubytes = 0, total = 0;
+    // every chunk is rounded up to 16 bytes in the pool
+    uint64_t pool_units = (enc->pool_ratio > 0 ? (uint64_t)(raw_bytes * enc->pool_ratio) : raw_bytes / 3) / 16 + n_chunks + 4096;
+    uint64_t ubytes = 0, total = 0, pool_used = 0;
     CK(enc->file_off.reserve((size_t)(n + 1) * 8), "alloc file offsets");
-    CK(enc->h_small.reserve(64 + (size_t)(n + 1) * 8), "alloc readback");
+    CK(enc->h_small.reserve(128 + (size_t)(n + 1) * 8), "alloc readback");
     b.file_off = enc->file_off.as<unsigned long long>();
     b.status = enc->status.as<unsigned long long>();
     b.n_segs_total = n_segs;
+    bool coded = false;
     for (int attempt = 0;; ++attempt) {
         ucap = (ucap + kStuffChunk - 1) / kStuffChunk * kStuffChunk;
-        const uint64_t n_chunks = ucap / kStuffChunk;
+        const uint64_t n_pieces = ucap / kStuffChunk;
         CK(enc->ustream.reserve(ucap + 64), "alloc unstuffed stream");
         CK(enc->raw_mask.reserve((ucap / 32 + 2) * 4), "alloc raw mask");
-        CK(enc->ffcount.reserve((n_chunks + 1) * 4), "alloc ff counts");
-        CK(enc->ffpos.reserve((n_chunks + 2) * 8), "alloc ff positions");
-        CK(enc->scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(n_chunks, std::max(n_visits, n_segs)))), "alloc scan scratch");
+        CK(enc->ffcount.reserve((n_pieces + 1) * 4), "alloc ff counts");
+        CK(enc->ffpos.reserve((n_pieces + 2) * 8), "alloc ff positions");
+        CK(enc->scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(n_pieces, std::max(n_chunks, n_segs)))), "alloc scan scratch");
+        CK(enc->pool.reserve(pool_units * 16), "alloc chunk pool");
         DevBuf &outb = enc->out_slot ? enc->out2 : enc->out;
         CK(outb.reserve(ocap + 64), "alloc output");
+        b.pool = enc->pool.as<uint32_t>();
+        b.pool_cap = pool_units;
         b.ustream = enc->ustream.as<uint8_t>();
         b.raw_mask = enc->raw_mask.as<uint32_t>();
         b.ffcount = enc->ffcount.as<uint32_t>();
@@ -318,18 +319,28 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         b.out = outb.as<uint8_t>();
         b.ustream_cap = ucap;
         b.out_cap = ocap;
-        CK(cudaMemsetAsync(b.status, 0, 32, st), "clear status");
+        if (!coded) {
+            StageTimer t(enc, 2);
+            CK(cudaMemsetAsync(b.status, 0, kStatusWords * 8, st), "clear status");
+            CK(launch_encode_chunks(b, hp, n, coder, st), "coding launch");
+            CK(launch_exclusive_scan(b.chunk_bits, b.chunk_bitpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "chunk position scan");
+            CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
+            CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches, scan_err), "segment position scan");
+            enc->launches += 2;
+        } else {
+            CK(cudaMemsetAsync(b.status, 0, 4 * 8, st), "clear status"); // keeps the pool cursor
+        }
         {
             StageTimer t(enc, 3);
             CK(launch_zero_ustream(b, n_segs, st), "zero stream launch");
             CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
-            CK(launch_emit_bits(b, hp, n, st), "emit launch");
+            CK(launch_place_chunks(b, hp, n, st), "placement launch");
             enc->launches += 3;
         }
         {
             StageTimer t(enc, 4);
             CK(launch_count_ff(b, st), "count ff launch");
-            CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "ff scan");
+            CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_pieces, b.scan_tmp, st, &enc->launches, scan_err), "ff scan");
             CK(launch_stuff_scatter(b, st), "scatter launch");
             CK(launch_file_offsets(b, hp, n, st), "file offsets launch");
             enc->launches += 3;
@@ -341,31 +352,40 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
                 enc->launches += 1;
                 CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
             }
-            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 32, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
-            CK(cudaMemcpyAsync(enc->h_small.p, b.status, 24, cudaMemcpyDeviceToHost, st), "read status");
-            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 24, scan_err, 8, cudaMemcpyDeviceToHost, st), "read scan flag");
+            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 128, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
+            CK(cudaMemcpyAsync(enc->h_small.p, b.status, kStatusWords * 8, cudaMemcpyDeviceToHost, st), "read status");
+            CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + kStatusWords * 8, scan_err, 8, cudaMemcpyDeviceToHost, st), "read scan flag");
         }
         CK(cudaStreamSynchronize(st), "final sync");
         const uint64_t *status = enc->h_small.as<uint64_t>();
-        if (status[3]) return fail(enc, JPGB_ERR_CUDA, "internal: prefix-sum look-back timed out");
+        if (status[kStatusWords] || status[3]) return fail(enc, JPGB_ERR_CUDA, "internal: prefix-sum look-back timed out");
+        if (status[2] & 8) return fail(enc, JPGB_ERR_BAD_PARAMS, "a scan segment exceeds 4 GiB (use a restart interval)");
         ubytes = status[0];
+        pool_used = status[5];
         if (status[2] == 0) {
             total = ubytes + status[1];
             break;
         }
-        if (attempt >= 2) return fail(enc, JPGB_ERR_CUDA, "internal: stream capacity retry did not converge");
-        // overflow: the sizing results are still on the device; redo the tail with room to spare
+        if (attempt >= 3) return fail(enc, JPGB_ERR_CUDA, "internal: buffer capacity retry did not converge");
+        // overflow: the sizing results are still on the device; redo what did not fit with room to spare
+        if (status[2] & 4) { // the pool: code again (the cursor counted every request, so the exact need is known)
+            pool_units = pool_used + pool_used / 64 + 4096;
+            coded = false;
+        } else {
+            coded = true;
+        }
         if (status[2] & 1) {
             ucap = ubytes + ubytes / 16 + 65536;
             ocap = ucap + ucap / 8 + 4096; // the 0xFF count is not known yet: generous
-        } else {
+        } else if (status[2] & 2) {
             ocap = ubytes + status[1] + 4096;
         }
     }
+    enc->pool_ratio = std::max(enc->pool_ratio * 0.98, 1.1 * (double)((pool_used > n_chunks ? pool_used - n_chunks : 0) * 16) / (double)std::max<uint64_t>(raw_bytes, 1));
     enc->ucap_ratio = std::max(enc->ucap_ratio * 0.98, 1.15 * (double)ubytes / (double)std::max<uint64_t>(raw_bytes, 1));
     CK(cudaStreamSynchronize(st), "final sync");
     if (piece_offsets) piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
-    offsets.assign(enc->h_small.as<uint64_t>() + 4, enc->h_small.as<uint64_t>() + 4 + n + 1);
+    offsets.assign(enc->h_small.as<uint64_t>() + 16, enc->h_small.as<uint64_t>() + 16 + n + 1);
     enc->out_total = total;
     if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
     return JPGB_OK;
@@ -410,7 +430,6 @@ int encode_host_pipelined(jpgb_encoder *enc, const Plan &plan, const uint8_t *co
     const size_t img_bytes = (size_t)plan.p.width * plan.p.height * plan.bpp;
     const size_t stride = (img_bytes + 255) & ~(size_t)255;
     uint32_t chunk = (uint32_t)std::max<size_t>(1, (96u << 20) / stride); // ~96 MB of pixels per chunk
-    if (plan.p.optimize_huffman) chunk = std::min<uint32_t>(chunk, 16);  // one histogram launch per image
     chunk = std::min(chunk, n);
     const uint32_t n_chunks = (n + chunk - 1) / chunk;
     CK(enc->pixels.reserve(stride * chunk), "alloc pixels");
@@ -562,7 +581,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->nbits, &e->slots, &e->bitpos, &e->seglen, &e->segpos,
+    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->scratch, &e->pool, &e->chunk_bits, &e->chunk_pool, &e->chunk_bitpos, &e->seglen, &e->segpos,
                       &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status, &e->scan_err};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
@@ -815,7 +834,7 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     int16_t *edge = reinterpret_cast<int16_t *>(enc->h_hist.as<uint8_t>() + hist_bytes);
     std::memset(edge, 0, 16);
     for (int c = 0; c < plan.ncomp; ++c) {
-        const uint64_t first = plan.block_off[c], last = plan.block_off[c] + (uint64_t)(plan.true_h[c] - 1) * plan.pad_w[c] + plan.true_w[c] - 1;
+        const uint64_t first = plan.block_off[c], last = plan.block_off[c] + (uint64_t)plan.true_w[c] * plan.true_h[c] - 1; // raster of the true grid
         CK(cudaMemcpyAsync(edge + c, enc->coef.as<int16_t>() + first * 64, 2, cudaMemcpyDeviceToHost, st), "read edge DC");
         CK(cudaMemcpyAsync(edge + 4 + c, enc->coef.as<int16_t>() + last * 64, 2, cudaMemcpyDeviceToHost, st), "read edge DC");
     }
@@ -872,8 +891,15 @@ int jpgb_coef_layout_for(const jpgb_params *p, jpgb_coef_layout *l) {
         l->true_w[c] = plan.true_w[c];
         l->true_h[c] = plan.true_h[c];
         l->block_offset[c] = plan.block_off[c];
+        l->slot_base[c] = plan.slot_base[c];
+        l->comp_h[c] = plan.comps[c].h;
+        l->comp_v[c] = plan.comps[c].v;
     }
     l->blocks_per_image = plan.blocks_per_image;
+    l->mcu_order = plan.mode == Mode::Interleaved;
+    l->mcu_cols = plan.mcu_cols;
+    l->mcu_rows = plan.mcu_rows;
+    l->blocks_per_mcu = plan.bpu_interleaved;
     return JPGB_OK;
 }
 

@@ -53,7 +53,13 @@ struct StageAParams {
     int n_images;
     int planar;            // 1: pixels = ncomp full-resolution planes of width*height bytes (plane_stride apart)
     unsigned long long plane_stride;
-    int use_fast;          // 1: stage_a_fast_kernel (task_h then holds the 32-block sub-run index)
+    int use_fast;          // 1: stage_a_warp_kernel
+    // Coefficient layout. mcu_order = 1 (interleaved scan): blocks in the order the scan codes
+    // them, block = (mcu * bpu + slot). mcu_order = 0: per component the raster of its TRUE grid (comp_tw x comp_th,
+    // the one encode_blocks walks), components back to back; blocks of the MCU padding are not stored.
+    int mcu_order, bpu;
+    int slot_base[4];      // first slot of the component inside the MCU (mcu_order)
+    int comp_tw[4], comp_th[4];
     // per warp task inside a group: component and block position inside the MCU
     int8_t task_comp[kMaxSlots], task_v[kMaxSlots], task_h[kMaxSlots];
     int comp_h[4], comp_v[4], comp_qt[4], comp_pw[4];
@@ -64,24 +70,40 @@ struct StageAParams {
 struct DevScan {
     int comp, ss, se;
     unsigned n_units, bpu;
-    FastDiv div_bpu;
-    unsigned long long visit_base;
     unsigned seg_base, n_segs;
+    unsigned chunk_base;        // first chunk of this scan inside one image
     unsigned sos_off, sos_len;  // into DevPlan::blob
     unsigned rst_base;          // restart segments of this scan that lie before this strip (0 for a whole image)
 };
 
+// Scans that code the same blocks in the same order: the single interleaved scan, or all scans of one component
+// (one in sequential mode; the DC scan and every AC band in progressive mode). A coding CTA stages the blocks of
+// one *chunk* once and codes them for every scan of the group.
+struct DevGroup {
+    int comp;                       // -1: interleaved
+    unsigned bpu;                   // blocks per unit (MCU): 1 unless interleaved
+    unsigned long long n_visits;    // blocks the group walks = n_units * bpu
+    unsigned long long block_base;  // first block of the group in one image's coefficient buffer
+    unsigned seg_visits;            // visits per restart segment (n_visits when restarts are off)
+    unsigned n_segs, cps;           // segments, chunks per segment
+    unsigned item_base;             // first work item of the group inside one image
+    FastDiv div_cps, div_bpu;
+};
+
 struct DevPlan {
     int n_scans, ncomp, n_slots, restart;   // restart interval in units (0 = off)
+    int n_groups, spg;                      // groups, scans per group: scan index = group + j * n_groups
+    int chunk_T;                            // visits per chunk = threads of the coding CTA (32 / 64 / 128 / 256)
+    int mcu_order;
     unsigned mcu_cols;
-    unsigned long long visits_per_image, blocks_per_image;
-    unsigned segs_per_image;
+    unsigned long long blocks_per_image;
+    unsigned segs_per_image, chunks_per_image, items_per_image;
     int has_eoi;            // 0 for every strip but the last
-    int8_t slot_comp[kMaxSlots], slot_v[kMaxSlots], slot_h[kMaxSlots];
-    int comp_h[4], comp_v[4], comp_tbl[4];
-    unsigned comp_pw[4], comp_tw[4];   // padded / true blocks per row
-    FastDiv div_tw[4], div_mcu_cols, div_restart, div_vpi; // div_vpi.d == 0: visits_per_image needs 64 bits
-    unsigned long long comp_off[4];
+    int8_t slot_comp[kMaxSlots];
+    uint8_t slot_back[kMaxSlots];   // interleaved: distance (in blocks of the MCU-ordered buffer) to the DC predecessor
+    uint8_t slot_first[kMaxSlots];  // 1: first block of its component inside the MCU (predictor resets at restarts)
+    int comp_tbl[4];
+    DevGroup groups[4];
     DevScan scans[kMaxScans];
     unsigned char blob[kMaxScans * 10]; // SOS segments of scans 1.. (10 bytes each: single component)
 };

@@ -6,49 +6,33 @@
 //   the MCU / block walks with restart bookkeeping           src/encoder.rs:727-804, 823-861, 885-972
 //   optimize_huffman_table's symbol histogram                src/encoder.rs:1086-1200
 //
-// Vocabulary. A *visit* is one block coded in one scan (a block is visited once per scan that
-// touches it); visits are numbered in the reference's emission order. A *segment* is the run of
-// visits between two restart points of one scan (one segment per scan when restarts are off);
-// its bits start byte-aligned and end padded with 1-bits. The *unstuffed stream* is the complete
-// file before 0xFF stuffing: per image the header, then per segment its lead (RSTn marker or the
-// next scan's SOS) and its data bytes, then EOI. `raw_mask` flags header/marker bytes so that the
-// stuffing pass leaves their 0xFF alone.
+// Vocabulary. A *visit* is one block coded in one scan. A *segment* is the run of visits between two restart
+// points of one scan (one segment per scan when restarts are off); its bits start byte-aligned and end padded
+// with 1-bits. A *chunk* is the code of <= chunk_T consecutive visits of one segment: one bit string. A *group*
+// is the set of scans that walk the same blocks (a component's DC scan and AC bands in progressive mode).
+// The *unstuffed stream* is the complete file before 0xFF stuffing: per image the header, then per segment its
+// lead (RSTn marker or the next scan's SOS) and its data bytes, then EOI. `raw_mask` flags header/marker bytes
+// so that the stuffing pass leaves their 0xFF alone.
 //
-//   encode_visits_kernel visit -> its code bits (in a slot) and their count (DC differencing, run/size symbols)
-//   [exclusive scan]     bit position of every visit
+//   encode_chunks_kernel persistent; a CTA takes a chunk, stages its blocks once (the coefficient buffer is laid
+//                        out in scan order, so they are one contiguous run), codes every visit for every scan of
+//                        the group, prefix-sums the bit counts inside the CTA and writes each scan's chunk as one
+//                        contiguous bit string into `pool` (+ its bit count)
+//   [exclusive scan]     bit position of every chunk (one element per chunk, not per block)
 //   segment_len_kernel   segment -> lead + ceil(bits/8) + tail bytes
 //   [exclusive scan]     byte position of every segment in the unstuffed stream
 //   segment_lead_kernel  writes headers / RSTn / SOS / EOI, sets raw_mask
-//   place_bits_kernel    slot bits shifted into the unstuffed stream, pad bits at segment end
-//   count_ff_kernel      chunk -> number of data 0xFF bytes
+//   place_chunks_kernel  streams every chunk from `pool` to its bit position (funnel shift), pad bits at segment end
+//   count_ff_kernel      4 KB piece of the stream -> number of data 0xFF bytes
 //   [exclusive scan]
 //   stuff_scatter_kernel copies every byte to its final place, inserting 0x00 after data 0xFF
+#include <mutex>
+
 #include "kernels.h"
 
 namespace jpgb {
 namespace {
 
-struct VisitInfo {
-    const int16_t *blk;   // this block's 64 zig-zag coefficients
-    const int16_t *pred;  // block holding the DC predictor, or nullptr for "predictor is 0"
-    int comp, ss, se, tbl;
-    int pred_back;        // the predecessor block is the block of visit (this - pred_back)
-    unsigned long long first_visit_of_seg; // within the image
-    unsigned seg_local;                    // segment index within the image
-    unsigned seg_in_scan;
-    int scan;
-    bool last_of_seg;
-};
-
-__device__ __forceinline__ int find_scan_by_visit(const DevPlan &P, unsigned long long v) {
-    int lo = 0, hi = P.n_scans - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (P.scans[mid].visit_base <= v) lo = mid;
-        else hi = mid - 1;
-    }
-    return lo;
-}
 __device__ __forceinline__ int find_scan_by_seg(const DevPlan &P, unsigned s) {
     int lo = 0, hi = P.n_scans - 1;
     while (lo < hi) {
@@ -58,90 +42,14 @@ __device__ __forceinline__ int find_scan_by_seg(const DevPlan &P, unsigned s) {
     }
     return lo;
 }
-
-// g = img * visits_per_image + v. Nearly every call has both numbers below 2^32 (FastDiv); the 64-bit
-// divide is ~100 instructions.
-__device__ __forceinline__ void split_visit(const DevPlan &P, unsigned long long g, unsigned long long &img, unsigned long long &v) {
-    if ((g >> 32) == 0 && P.div_vpi.d != 0) {
-        unsigned q, r;
-        divmod((unsigned)g, P.div_vpi, q, r);
-        img = q;
-        v = r;
-    } else {
-        img = g / P.visits_per_image;
-        v = g - img * P.visits_per_image;
+__device__ __forceinline__ int find_scan_by_chunk(const DevPlan &P, unsigned c) {
+    int lo = 0, hi = P.n_scans - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.scans[mid].chunk_base <= c) lo = mid;
+        else hi = mid - 1;
     }
-}
-// unit and slot of a visit inside its scan; a scan has < 2^32 visits (<= 2^26 blocks x 18 per unit)
-__device__ __forceinline__ void split_unit(const DevScan &S, unsigned long long v, unsigned &unit, unsigned &slot) {
-    const unsigned rel = (unsigned)(v - S.visit_base);
-    if (S.bpu == 1) {
-        unit = rel;
-        slot = 0;
-    } else {
-        divmod(rel, S.div_bpu, unit, slot);
-    }
-}
-
-// Where does visit `v` (numbered within one image) live, and what precedes it?
-// Interleaved order: encoder.rs:747-791 (MCU raster; component, v, h inside the MCU).
-// Single-component order: encoder.rs:832 / 894 / 946 over encode_blocks' raster grid (:1030-1031).
-// Predictor reset at restart points: :753-756, :838, :900.
-__device__ __forceinline__ VisitInfo locate_visit(const DevPlan &P, const int16_t *coef_img, unsigned long long v) {
-    VisitInfo r;
-    const int k = find_scan_by_visit(P, v);
-    const DevScan &S = P.scans[k];
-    unsigned unit, slot;
-    split_unit(S, v, unit, slot);
-    const unsigned R = (unsigned)P.restart;
-    unsigned seg_q = 0, seg_r = unit; // unit = seg_q * R + seg_r
-    if (R) divmod(unit, P.div_restart, seg_q, seg_r);
-    const bool restart_here = unit == 0 || (R && seg_r == 0);
-    unsigned long long blk, pred = 0;
-    bool has_pred = true;
-    int comp;
-    if (S.comp < 0) {
-        comp = P.slot_comp[slot];
-        const unsigned bv = P.slot_v[slot], bh = P.slot_h[slot];
-        const unsigned H = P.comp_h[comp], V = P.comp_v[comp], pw = P.comp_pw[comp];
-        unsigned my, mx;
-        divmod(unit, P.div_mcu_cols, my, mx);
-        const unsigned long long off = P.comp_off[comp];
-        blk = off + (unsigned long long)(my * V + bv) * pw + mx * H + bh;
-        r.pred_back = (bh > 0 || bv > 0) ? 1 : (int)(S.bpu - H * V + 1);
-        if (bh > 0) pred = blk - 1;
-        else if (bv > 0) pred = off + (unsigned long long)(my * V + bv - 1) * pw + mx * H + (H - 1);
-        else if (restart_here) has_pred = false;
-        else { // last block of this component in the previous MCU
-            const unsigned pmy = mx ? my : my - 1, pmx = mx ? mx - 1 : P.mcu_cols - 1;
-            pred = off + (unsigned long long)(pmy * V + V - 1) * pw + pmx * H + (H - 1);
-        }
-    } else {
-        comp = S.comp;
-        r.pred_back = 1;
-        const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
-        const unsigned long long off = P.comp_off[comp];
-        unsigned by, bx;
-        divmod(unit, P.div_tw[comp], by, bx);
-        blk = off + (unsigned long long)by * pw + bx;
-        if (restart_here) has_pred = false;
-        else { // previous block of the raster grid
-            const unsigned pby = bx ? by : by - 1, pbx = bx ? bx - 1 : tw - 1;
-            pred = off + (unsigned long long)pby * pw + pbx;
-        }
-    }
-    r.blk = coef_img + blk * 64;
-    r.pred = has_pred ? coef_img + pred * 64 : nullptr;
-    r.comp = comp;
-    r.ss = S.ss;
-    r.se = S.se;
-    r.tbl = P.comp_tbl[comp];
-    r.scan = k;
-    r.seg_in_scan = seg_q;
-    r.seg_local = S.seg_base + r.seg_in_scan;
-    r.first_visit_of_seg = S.visit_base + (unsigned long long)r.seg_in_scan * R * S.bpu;
-    r.last_of_seg = slot == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
-    return r;
+    return lo;
 }
 
 // get_code, writer.rs:455-470: size = bit length of |v|, bits = low `size` bits of (v - (v<0))
@@ -161,35 +69,30 @@ __device__ __forceinline__ unsigned nonzero16x2(unsigned x) {
     return r;
 }
 
-// Bit sink of one visit. Codes are packed MSB-first into 32-bit words. Slots are tiled by kSlotTile
-// visits (one coding CTA): word j of visit g lives at slot_of(g)[j * kSlotTile], so the lanes of a warp
-// write one contiguous line per word and a CTA's slots are one contiguous 56 KB region. (Word-major
-// across the whole launch, planes n_visits words apart, made every CTA touch a dozen pages hundreds of
-// MB apart and the coding kernel TLB-bound.) The visit is coded exactly once; where its bits belong in
-// the stream is decided later, from the prefix sum of the totals, by place_bits_kernel.
-__device__ __forceinline__ uint32_t *slot_of(uint32_t *slots, unsigned long long g) {
-    return slots + (g / kSlotTile) * (kSlotTile * kSlotWords) + (g % kSlotTile);
-}
-
+// Bit sink of one visit. Codes are packed MSB-first into 32-bit words; word j of the visit with index i inside
+// its chunk goes to scratch[j * T + i] (the lanes of a warp write one contiguous line per word). The scratch of a
+// coding CTA is T x kSlotWords words that it overwrites chunk after chunk, so it stays in L2. Where the bits
+// belong in the chunk is decided after all visits of the chunk are coded, from the prefix sum of their lengths.
+template <int T>
 struct BitSink {
     unsigned long long acc = 0;
     int n = 0;
     unsigned off = 0; // bytes written so far, scaled by the tile stride
     uint32_t *slot0;
 
-    __device__ __forceinline__ BitSink(uint32_t *slots, unsigned long long g) : slot0(slot_of(slots, g)) {}
+    __device__ __forceinline__ BitSink(uint32_t *scratch, int visit) : slot0(scratch + visit) {}
     __device__ __forceinline__ void put(uint32_t code, int len) { // len <= 31, n < 32 on entry
         acc = (acc << len) | code;
         n += len;
         if (n >= 32) {
             n -= 32;
             *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(slot0) + off) = (uint32_t)(acc >> n);
-            off += kSlotTile * 4;
+            off += T * 4;
         }
     }
     __device__ __forceinline__ unsigned finish() {
         if (n > 0) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(slot0) + off) = (uint32_t)(acc << (32 - n)); // left-aligned tail
-        return off / (kSlotTile * 4) * 32 + n;
+        return off / (T * 4) * 32 + n;
     }
 };
 
@@ -199,23 +102,8 @@ struct BitSink {
 // size << 27: only the value bits are written (release-build behaviour of the reference).
 constexpr uint32_t kCodeBits = 0x07FFFFFFu;
 
-constexpr int kEncThreads = kSlotTile;
-constexpr int kStageStride = 72; // int16 per staged block: 128 B of coefficients + 16 B pad (128-bit rows stay conflict-free)
-
-struct __align__(16) EncodeShared {
-    int16_t coef[kEncThreads * kStageStride]; // the CTA's blocks, staged with coalesced loads
-    unsigned long long ptr_or_mask[kEncThreads]; // first the block address | group range, then the non-zero mask
-    uint32_t first[kEncThreads];  // the DC code of the visit (table-word format), 0 in AC scans
-    uint32_t info[kEncThreads];   // se | first_ac << 8 | table << 16 | valid << 24
-    uint32_t ac_tab[2 * 256];
-    uint32_t dc_tab[2 * 16];
-    uint32_t bin[64];
-    uint16_t order[kEncThreads];
-};
-
-__device__ __forceinline__ const uint32_t *huff_for(const EntropyBuffers &b, unsigned long long img, int tbl, int cls) {
-    return b.huff + (b.huff_per_image ? img * kHuffWordsPerImage : 0) + (size_t)(tbl * 2 + cls) * 256;
-}
+constexpr int kStageStride = 72;    // int16 per staged block: 128 B of coefficients + 16 B pad (128-bit rows stay conflict-free)
+constexpr int kAsmWordsProg = 3072; // progressive: words of the chunk assembly buffer (the staged blocks stay live across the group's scans)
 
 // Zero runs longer than 15 in front of a non-zero coefficient take one ZRL symbol per 16 zeros (writer.rs:369-373).
 // `m` has bit k set for every non-zero coefficient k of the band [first_ac, se]. Returns the positions of the
@@ -243,8 +131,8 @@ __device__ __forceinline__ unsigned long long zrl_markers(unsigned long long m, 
 // zig-zag order is the highest set bit (one FLO, no bit reversal). One iteration per set bit: a non-zero
 // coefficient, or a ZRL marker (zrl_markers): a zero 15 positions after the start of its run, for which the same
 // arithmetic yields the symbol 0xF0 with no value bits (writer.rs:369-373), so the loop has no ZRL branch.
-template <int BASE>
-__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint32_t *__restrict__ tab, BitSink &sink) {
+template <int BASE, int T>
+__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint32_t *__restrict__ tab, BitSink<T> &sink) {
 #pragma unroll 1
     while (m) {
         int p;
@@ -264,114 +152,154 @@ __device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shar
         sink.put((e & kCodeBits) | bits, (int)(e >> 27));
     }
 }
+template <int T>
 __device__ __forceinline__ void code_nonzeros(unsigned lo_rev, unsigned hi_rev, int first_ac, int se, const int16_t *__restrict__ c,
-                                              const uint32_t *__restrict__ tab, BitSink &sink) {
+                                              const uint32_t *__restrict__ tab, BitSink<T> &sink) {
     int next = first_ac;
     const unsigned c_shared = (unsigned)__cvta_generic_to_shared(c);
-    code_half<0>(lo_rev, next, c_shared, tab, sink);
-    code_half<32>(hi_rev, next, c_shared, tab, sink);
+    code_half<0, T>(lo_rev, next, c_shared, tab, sink);
+    code_half<32, T>(hi_rev, next, c_shared, tab, sink);
     if (next <= se) { // the band ends in zeros: EOB (writer.rs:383-385)
         const uint32_t e = tab[0];
         sink.put(e & kCodeBits, (int)(e >> 27));
     }
 }
 
-// write_dc + write_ac_block for 256 consecutive visits per CTA, in three steps:
-//  1. every thread locates its visit; each warp copies its 32 blocks into shared memory with
-//     coalesced 128-bit loads (8 lanes per block);
-//  2. every thread builds the 64-bit mask of non-zero coefficients of its block inside the scan's band
-//     and the DC code; the CTA sorts its visits by their number of non-zeros (counting sort);
-//  3. thread t codes the visit of rank t: the lanes of a warp then run nearly the same number of
-//     iterations of the per-coefficient loop, which is where the time goes.
-// FULL: every scan of the plan covers the whole block (baseline and sequential modes), so the band
-// bookkeeping is constant.
-template <bool FULL>
-__global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
-    __shared__ EncodeShared sh;
+// what thread 0 works out for the CTA's next chunk
+struct __align__(16) ItemInfo {
+    unsigned long long img, blk0, chunk_index0; // first block of the chunk (global); img * chunks_per_image + seg * cps + chunk
+    unsigned v_in_seg0, n_valid, group;
+    int done;
+};
+
+// shared-memory carve-up of the coding CTA
+template <int T, bool FULL>
+struct CoderSmem {
+    static constexpr int kCoefBytes = T * kStageStride * 2;
+    static constexpr int kAsmWords = FULL ? kCoefBytes / 4 : kAsmWordsProg; // FULL: the staged blocks are dead once coded -> reuse
+    static constexpr int oAsm = FULL ? 0 : kCoefBytes;
+    static constexpr int oMask = kCoefBytes + (FULL ? 0 : kAsmWordsProg * 4);
+    static constexpr int oAc = oMask + T * 8;
+    static constexpr int oDc = oAc + 2048;
+    static constexpr int oBin = oDc + 128;
+    static constexpr int oNb = oBin + 256;
+    static constexpr int oFirst = oNb + T * 4;
+    static constexpr int oInfo = oFirst + T * 4;
+    static constexpr int oOrder = oInfo + T * 4;
+    static constexpr int oWsum = oOrder + T * 2;
+    static constexpr int oItem = oWsum + 64;
+    static constexpr int kBytes = oItem + 64;
+};
+
+// write_dc + write_ac_block for one chunk after the other (persistent CTAs, a ticket per chunk):
+//  1. the chunk's blocks -- one contiguous run of the scan-ordered coefficient buffer -- are copied into shared
+//     memory with coalesced 16-byte cp.async; every thread then owns visit `tid`: the 64-bit mask of its non-zero
+//     coefficients and its DC difference (the predecessor is a fixed distance back in the same run);
+//  then for every scan of the group (one, except in progressive mode: DC scan and AC bands share the staging):
+//  2. band mask + ZRL markers; the CTA sorts its visits by their number of symbols (counting sort);
+//  3. thread t codes the visit of rank t -- the lanes of a warp then run nearly the same number of iterations of
+//     the per-coefficient loop, which is where the time goes -- into the CTA's L2-resident scratch;
+//  4. prefix sum of the visits' bit counts, then every thread shifts its visit's words to their place in the
+//     chunk's bit string, assembled in shared memory and written to `pool` with coalesced 128-bit stores.
+// FULL: every scan of the plan covers the whole block (baseline and sequential modes).
+template <int T, bool FULL>
+__global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b, unsigned long long n_items) {
+    using L = CoderSmem<T, FULL>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    int16_t *coef = reinterpret_cast<int16_t *>(smem);
+    uint32_t *asmbuf = reinterpret_cast<uint32_t *>(smem + L::oAsm);
+    unsigned long long *maskv = reinterpret_cast<unsigned long long *>(smem + L::oMask);
+    uint32_t *ac_tab = reinterpret_cast<uint32_t *>(smem + L::oAc);
+    uint32_t *dc_tab = reinterpret_cast<uint32_t *>(smem + L::oDc);
+    uint32_t *bin = reinterpret_cast<uint32_t *>(smem + L::oBin);
+    uint32_t *nbv = reinterpret_cast<uint32_t *>(smem + L::oNb);
+    uint32_t *firstv = reinterpret_cast<uint32_t *>(smem + L::oFirst);
+    uint32_t *infov = reinterpret_cast<uint32_t *>(smem + L::oInfo);
+    uint16_t *order = reinterpret_cast<uint16_t *>(smem + L::oOrder);
+    uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + L::oWsum); // [0..7] warp sums, [8] pool offset of the chunk
+    ItemInfo *item = reinterpret_cast<ItemInfo *>(smem + L::oItem);
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long cta_base = (unsigned long long)blockIdx.x * kEncThreads;
-    const unsigned long long g = cta_base + tid;
-    const bool valid = g < n_visits;
     const DevPlan &P = *b.plan;
+    uint32_t *scratch = b.scratch + (size_t)blockIdx.x * (T * kSlotWords);
+    long long tab_img = -1; // whose Huffman tables the shared copy holds
+    for (int i = tid; i < 64; i += T) bin[i] = 0;
 
-    // AC tables of the CTA's first image into shared memory; a CTA that spans images with their own
-    // (optimized) tables reads them from global memory instead
-    unsigned long long img_first = 0, img_last = 0, tmp;
-    if (b.huff_per_image) {
-        split_visit(P, cta_base, img_first, tmp);
-        split_visit(P, (cta_base + kEncThreads < n_visits ? cta_base + kEncThreads : n_visits) - 1, img_last, tmp);
-    }
-    const bool shared_tables = img_first == img_last;
-    // the table words travel through registers: loaded here, stored to shared memory just before the first CTA
-    // barrier, so their latency hides behind locating and staging
-    static_assert(kEncThreads == 256, "two AC words and at most one DC word per thread");
-    uint32_t tab_ac0 = 0, tab_ac1 = 0, tab_dc = 0;
-    if (shared_tables) {
-        const uint32_t *set = b.huff + img_first * kHuffWordsPerImage;
-        tab_ac0 = __ldg(set + 256 + tid);       // table 0, AC
-        tab_ac1 = __ldg(set + 512 + 256 + tid); // table 1, AC
-        if (tid < 32) tab_dc = __ldg(set + (tid >> 4) * 512 + (tid & 15)); // DC categories 0..15 of both tables
-    }
-    if (tid < 64) sh.bin[tid] = 0;
-
-    // ---- 1. locate, stage ----
-    unsigned long long img = 0, v = 0;
-    VisitInfo vi{};
-    int w_lo = 1, w_hi = 0, first_ac = 1;
-    unsigned long long where = 0;
-    if (valid) {
-        split_visit(P, g, img, v);
-        vi = locate_visit(P, b.coef + img * P.blocks_per_image * 64, v);
-        first_ac = FULL || vi.ss == 0 ? 1 : vi.ss;
-        w_lo = FULL ? 0 : vi.ss >> 3;
-        w_hi = FULL ? 7 : vi.se >> 3;
-        where = (unsigned long long)vi.blk | (unsigned)w_lo | (unsigned)(w_hi << 3); // blocks are 128-byte aligned
-    }
-    if (!FULL && !__syncthreads_or(valid && vi.se > 0)) { // a CTA inside DC scans (progressive): one code per visit
-        if (valid) {
-            unsigned len = 0;
-            // se == 0 is a DC scan (ss == 0) or the *empty* first AC band that 34..64 progressive scans produce
-            // (64 / (scans - 1) == 1: band 0 = [1, 1), written as Ss=1, Se=0 -- encoder.rs:926-944): no bits at all
-            if (vi.ss == 0) {
-                const int prev = vi.pred ? (int)__ldg(vi.pred) : 0;
-                int size;
-                uint32_t bits;
-                value_code((int)(int16_t)(__ldg(vi.blk) - prev), size, bits);
-                const uint32_t e = __ldg(huff_for(b, img, vi.tbl, 0) + size) | bits;
-                len = e >> 27;
-                if (len) *slot_of(b.slots, g) = (e & kCodeBits) << (32 - len);
+    for (;;) {
+        __syncthreads(); // the previous chunk is completely written out
+        if (tid == 0) {
+            const unsigned long long it = atomicAdd(b.status + 4, 1ull);
+            ItemInfo ii{};
+            ii.done = it >= n_items;
+            if (!ii.done) {
+                const unsigned long long img = it / P.items_per_image;
+                unsigned r = (unsigned)(it - img * P.items_per_image);
+                int g = 0;
+                while (g + 1 < P.n_groups && r >= P.groups[g + 1].item_base) ++g;
+                const DevGroup &G = P.groups[g];
+                r -= G.item_base;
+                unsigned seg, chunk;
+                divmod(r, G.div_cps, seg, chunk);
+                const unsigned long long seg_start = (unsigned long long)seg * G.seg_visits;
+                const unsigned long long v0 = seg_start + (unsigned long long)chunk * T;
+                unsigned long long seg_end = seg_start + G.seg_visits;
+                if (seg_end > G.n_visits) seg_end = G.n_visits;
+                ii.img = img;
+                ii.group = (unsigned)g;
+                ii.v_in_seg0 = chunk * T;
+                ii.n_valid = v0 < seg_end ? (unsigned)(seg_end - v0 < (unsigned long long)T ? seg_end - v0 : T) : 0u;
+                ii.blk0 = img * P.blocks_per_image + G.block_base + v0;
+                ii.chunk_index0 = img * P.chunks_per_image + r;
             }
-            b.nbits[g] = len;
+            *item = ii;
         }
-        return;
-    }
-    sh.ptr_or_mask[tid] = where;
-    __syncwarp();
-    { // eight asynchronous 16-byte copies per lane, all in flight together
-        const int w = lane & 7;
+        __syncthreads();
+        const ItemInfo it = *item;
+        if (it.done) break;
+        if (it.n_valid == 0) { // a chunk slot past the end of a short last segment: it exists only as an (empty) descriptor
+            for (int j = tid; j < P.spg; j += T) {
+                const unsigned long long ci = it.chunk_index0 + P.scans[it.group + j * P.n_groups].chunk_base;
+                b.chunk_bits[ci] = 0;
+                b.chunk_pool[ci] = 0;
+            }
+            continue;
+        }
+        const DevGroup &G = P.groups[it.group];
+        const bool valid = (unsigned)tid < it.n_valid;
+
+        // Huffman tables of this image (or the shared default ones) -> shared memory, when they change
+        const long long want_tab = b.huff_per_image ? (long long)it.img : 0;
+        if (want_tab != tab_img) {
+            const uint32_t *set = b.huff + (size_t)want_tab * kHuffWordsPerImage;
+            for (int i = tid; i < 512; i += T) ac_tab[i] = __ldg(set + (i >> 8) * 512 + 256 + (i & 255)); // table 0 / 1, AC
+            if (tid < 32) dc_tab[tid] = __ldg(set + (tid >> 4) * 512 + (tid & 15));                        // DC categories 0..15
+            tab_img = want_tab;
+        }
+
+        // ---- 1. stage the chunk's blocks: n_valid * 128 contiguous bytes ----
+        const int16_t *src_blocks = b.coef + it.blk0 * 64;
+        {
+            const unsigned pieces = it.n_valid * 8;
+            const char *g = reinterpret_cast<const char *>(src_blocks) + (size_t)tid * 16;
+            unsigned d = (unsigned)__cvta_generic_to_shared(coef) + (tid >> 3) * (kStageStride * 2) + (tid & 7) * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int bi = warp * 32 + i * 4 + (lane >> 3);
-            const unsigned long long e = sh.ptr_or_mask[bi];
-            const uint4 *src = reinterpret_cast<const uint4 *>(e & ~127ull);
-            if (src != nullptr && (FULL || (w >= (int)(e & 7) && w <= (int)((e >> 3) & 7)))) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(sh.coef + bi * kStageStride + w * 8);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + w) : "memory");
+            for (int k = 0; k < 8; ++k) {
+                if ((unsigned)(tid + k * T) < pieces) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                g += T * 16;
+                d += (T / 8) * (kStageStride * 2);
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-    __syncwarp();
+        __syncthreads();
 
-    // ---- 2. mask of non-zeros in [first_ac, se], DC code, sort key ----
-    unsigned m_lo = 0, m_hi = 0; // bit-reversed: coefficient k is bit 31 - k % 32
-    uint32_t first = 0;
-    if (valid) {
-        const uint4 *mine = reinterpret_cast<const uint4 *>(sh.coef + tid * kStageStride);
-        if (FULL || vi.se > 0) {
+        // mask of all non-zero coefficients of this thread's block, its DC difference, its table
+        unsigned long long m_all = 0;
+        int dcdiff = 0, tbl = 0;
+        if (valid) {
+            const uint4 *mine = reinterpret_cast<const uint4 *>(coef + tid * kStageStride);
+            unsigned m_lo = 0, m_hi = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                if (!FULL && (w < w_lo || w > w_hi)) continue;
                 const uint4 q = mine[w];
                 // per 16-bit half min(x, 1) = (x != 0); dp2a weighs the two halves 1 and 2 and accumulates
                 unsigned byte = __dp2a_lo(nonzero16x2(q.x), 0x0201u, 0u);
@@ -381,69 +309,155 @@ __global__ void __launch_bounds__(kEncThreads) encode_visits_kernel(const Entrop
                 if (w < 4) m_lo |= byte << (8 * w);
                 else m_hi |= byte << (8 * (w - 4));
             }
-            unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
-            m &= FULL ? ~1ull : (~0ull << first_ac) & (~0ull >> (63 - vi.se));
-            m |= zrl_markers(m, first_ac);
-            m_lo = __brev((unsigned)m); // coded from the highest bit down
-            m_hi = __brev((unsigned)(m >> 32));
+            m_all = (((unsigned long long)m_hi << 32) | m_lo) & ~1ull;
+            // DC predictor (encoder.rs:753-756, 838, 900): the previous block of the component in scan order, 0 at a restart
+            const unsigned v_in_seg = it.v_in_seg0 + tid;
+            unsigned unit = v_in_seg, slot = 0;
+            if (G.bpu > 1) divmod(v_in_seg, G.div_bpu, unit, slot);
+            const int comp = G.comp < 0 ? P.slot_comp[slot] : G.comp;
+            tbl = P.comp_tbl[comp];
+            const int back = G.comp < 0 ? P.slot_back[slot] : 1;
+            const bool first_of_comp = G.comp < 0 ? P.slot_first[slot] != 0 : true;
+            int prev = 0;
+            if (!(unit == 0 && first_of_comp)) prev = tid >= back ? (int)coef[(tid - back) * kStageStride] : (int)__ldg(src_blocks + ((long long)tid - back) * 64);
+            dcdiff = (int)(int16_t)(coef[tid * kStageStride] - prev);
         }
-    }
-    const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
-    if (shared_tables) {
-        sh.ac_tab[tid] = tab_ac0;
-        sh.ac_tab[256 + tid] = tab_ac1;
-        if (tid < 32) sh.dc_tab[tid] = tab_dc;
-    }
-    __syncthreads();
-    if (valid && (FULL || vi.ss == 0)) { // write_dc, writer.rs:342-352
-        // The predecessor is the block of an earlier visit of this scan, a few visits back: staged by this CTA
-        // (all staging is complete after the barrier) unless this visit is among the CTA's first.
-        const int dc = sh.coef[tid * kStageStride];
-        const int prev = !vi.pred ? 0 : (tid >= vi.pred_back ? (int)sh.coef[(tid - vi.pred_back) * kStageStride] : (int)__ldg(vi.pred));
-        int size;
-        uint32_t bits;
-        value_code((int)(int16_t)(dc - prev), size, bits);
-        first = (shared_tables ? sh.dc_tab[vi.tbl * 16 + size] : __ldg(huff_for(b, img, vi.tbl, 0) + size)) | bits;
-    }
-    const unsigned rank = atomicAdd(&sh.bin[nnz], 1u);
-    sh.ptr_or_mask[tid] = ((unsigned long long)m_hi << 32) | m_lo;
-    sh.first[tid] = first;
-    sh.info[tid] = (unsigned)vi.se | ((unsigned)first_ac << 8) | ((unsigned)vi.tbl << 16) | (valid ? 1u << 24 : 0u);
-    __syncthreads();
-    { // exclusive prefix over the 64 bins, two per lane; every warp computes it for itself (no single-warp step)
-        const unsigned a = sh.bin[2 * lane], c = sh.bin[2 * lane + 1];
-        unsigned inc = a + c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        const unsigned even = inc - a - c, odd = inc - c; // first rank of bins 2*lane and 2*lane + 1
-        const unsigned e = __shfl_sync(0xffffffffu, even, nnz >> 1), o = __shfl_sync(0xffffffffu, odd, nnz >> 1);
-        sh.order[((nnz & 1) ? o : e) + rank] = (uint16_t)tid;
-    }
-    __syncthreads();
 
-    // ---- 3. code the visit of rank tid ----
-    const int src = sh.order[tid];
-    const unsigned info = sh.info[src];
-    if (!(info >> 24)) return;
-    const unsigned long long mask = sh.ptr_or_mask[src];
-    const uint32_t dc_code = sh.first[src];
-    const int se = FULL ? 63 : info & 0xFF, fa = FULL ? 1 : (info >> 8) & 0xFF, tbl = (info >> 16) & 0xFF;
-    BitSink sink(b.slots, cta_base + src);
-    sink.put(dc_code & kCodeBits, (int)(dc_code >> 27));
-    if (se > 0) {
-        const int16_t *c = sh.coef + src * kStageStride;
-        if (shared_tables) {
-            code_nonzeros((unsigned)mask, (unsigned)(mask >> 32), fa, se, c, sh.ac_tab + tbl * 256, sink);
-        } else {
-            unsigned long long simg, sv;
-            split_visit(P, cta_base + src, simg, sv);
-            code_nonzeros((unsigned)mask, (unsigned)(mask >> 32), fa, se, c, huff_for(b, simg, tbl, 1), sink);
+        for (int j = 0; j < (FULL ? 1 : P.spg); ++j) {
+            const DevScan &S = P.scans[it.group + j * P.n_groups];
+            const int ss = FULL ? 0 : S.ss, se = FULL ? 63 : S.se;
+            const int first_ac = ss == 0 ? 1 : ss;
+            // ---- 2. band mask with ZRL markers, DC code, sort key ----
+            unsigned m_lo = 0, m_hi = 0;
+            uint32_t first = 0;
+            if (valid) {
+                if (se > 0) {
+                    unsigned long long m = FULL ? m_all : m_all & (~0ull << first_ac) & (~0ull >> (63 - se));
+                    m |= zrl_markers(m, first_ac);
+                    m_lo = __brev((unsigned)m); // coded from the highest bit down
+                    m_hi = __brev((unsigned)(m >> 32));
+                }
+                if (ss == 0) { // write_dc, writer.rs:342-352
+                    int size;
+                    uint32_t bits;
+                    value_code(dcdiff, size, bits);
+                    first = dc_tab[tbl * 16 + size] | bits;
+                }
+            }
+            maskv[tid] = ((unsigned long long)m_hi << 32) | m_lo;
+            firstv[tid] = first;
+            infov[tid] = (unsigned)tbl | (valid ? 0x100u : 0u);
+            if (se > 0) {
+                const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
+                const unsigned rank = atomicAdd(&bin[nnz], 1u);
+                __syncthreads();
+                { // exclusive prefix over the 64 bins, two per lane; every warp computes it for itself
+                    const unsigned a = bin[2 * lane], c = bin[2 * lane + 1];
+                    unsigned inc = a + c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += o;
+                    }
+                    const unsigned even = inc - a - c, odd = inc - c; // first rank of bins 2*lane and 2*lane + 1
+                    const unsigned e = __shfl_sync(0xffffffffu, even, nnz >> 1), o = __shfl_sync(0xffffffffu, odd, nnz >> 1);
+                    order[((nnz & 1) ? o : e) + rank] = (uint16_t)tid;
+                }
+                __syncthreads();
+                for (int i = tid; i < 64; i += T) bin[i] = 0; // for the next sort (several barriers away)
+            } else {
+                order[tid] = (uint16_t)tid; // one code per visit at most: nothing to balance
+                __syncthreads();
+            }
+
+            // ---- 3. code the visit of rank tid ----
+            {
+                const int src = order[tid];
+                const unsigned inf = infov[src];
+                unsigned nb = 0;
+                if (inf & 0x100u) {
+                    const unsigned long long mask = maskv[src];
+                    const uint32_t dc_code = firstv[src];
+                    BitSink<T> sink(scratch, src);
+                    sink.put(dc_code & kCodeBits, (int)(dc_code >> 27));
+                    if (se > 0) code_nonzeros<T>((unsigned)mask, (unsigned)(mask >> 32), first_ac, se, coef + src * kStageStride, ac_tab + (inf & 0xFF) * 256, sink);
+                    nb = sink.finish();
+                }
+                nbv[src] = nb;
+            }
+            __syncthreads(); // all code words are in the scratch (visible to the CTA), all reads of the staged blocks are done
+
+            // ---- 4. bit offsets of the visits inside the chunk, assembly, write-out ----
+            const unsigned myb = nbv[tid];
+            const unsigned nw = (myb + 31) >> 5;
+            const uint32_t *mine = scratch + tid;
+            uint32_t pre[4]; // nearly every visit has at most four words: request them before the prefix sum
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[q] = __ldcg(mine + q * T);
+            unsigned inc = myb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            unsigned off = inc - myb, total = 0;
+#pragma unroll
+            for (int w = 0; w < T / 32; ++w) {
+                const unsigned sw = wsum[w];
+                if (w < warp) off += sw;
+                total += sw;
+            }
+            const unsigned total_words = (total + 31) >> 5;
+            const unsigned long long ci = it.chunk_index0 + S.chunk_base;
+            if (tid == 0) {
+                const unsigned units = (total_words + 3) >> 2; // 16-byte units
+                unsigned long long at = units ? atomicAdd(b.status + 5, (unsigned long long)units) : 0ull;
+                if (at + units > b.pool_cap) {
+                    atomicOr(b.status + 2, 4ull);
+                    at = ~0ull;
+                }
+                wsum[8] = (uint32_t)at;
+                wsum[9] = (uint32_t)(at >> 32);
+                b.chunk_bits[ci] = total;
+                b.chunk_pool[ci] = (uint32_t)at;
+            }
+            for (unsigned wb = 0; wb < total_words; wb += L::kAsmWords) {
+                const unsigned nwin = total_words - wb < (unsigned)L::kAsmWords ? total_words - wb : (unsigned)L::kAsmWords;
+                for (unsigned i = tid * 4; i < nwin; i += T * 4) *reinterpret_cast<uint4 *>(asmbuf + i) = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+                if (myb) { // shift this visit's words to bit offset `off` of the chunk; first and last word are shared with the neighbours
+                    const unsigned d0 = off >> 5, dl = (off + myb - 1) >> 5, sft = off & 31;
+                    const unsigned lo = d0 > wb ? d0 : wb, hi = dl < wb + nwin - 1 ? dl : wb + nwin - 1;
+                    if (lo <= hi) {
+                        unsigned jw = lo - d0; // source word that starts in destination word `lo`
+                        auto word = [&](unsigned q) -> uint32_t {
+                            if (q >= nw) return 0u;
+                            if (q < 4) return q == 0 ? pre[0] : (q == 1 ? pre[1] : (q == 2 ? pre[2] : pre[3]));
+                            return __ldcg(mine + q * T);
+                        };
+                        uint32_t prev = jw > 0 ? word(jw - 1) : 0u;
+                        for (unsigned d = lo; d <= hi; ++d, ++jw) {
+                            const uint32_t cur = word(jw);
+                            const uint32_t val = sft ? __funnelshift_r(cur, prev, sft) : cur;
+                            const bool owned = 32u * d >= off && 32u * d + 32u <= off + myb;
+                            if (owned) asmbuf[d - wb] = val;
+                            else atomicOr(asmbuf + (d - wb), val);
+                            prev = cur;
+                        }
+                    }
+                }
+                __syncthreads();
+                const unsigned long long at = ((unsigned long long)wsum[9] << 32) | wsum[8];
+                if (at != ~0ull) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(b.pool) + at + (wb >> 2);
+                    for (unsigned i = tid; i * 4 < nwin; i += T) dst[i] = reinterpret_cast<const uint4 *>(asmbuf)[i];
+                }
+                if (wb + L::kAsmWords < total_words || !FULL) __syncthreads(); // the buffer is reused
+            }
         }
     }
-    b.nbits[cta_base + src] = sink.finish();
 }
 
 // lead of local segment `s`: what the reference writes between the previous segment's last byte
@@ -465,13 +479,14 @@ __global__ void __launch_bounds__(256) segment_len_kernel(const EntropyBuffers b
     const int k = find_scan_by_seg(P, s);
     const DevScan &S = P.scans[k];
     const unsigned i = s - S.seg_base;
-    const unsigned long long span = (unsigned long long)P.restart * S.bpu;
-    const unsigned long long vf = S.visit_base + i * span;
-    const unsigned long long vn = (i + 1 < S.n_segs) ? vf + span : S.visit_base + (unsigned long long)S.n_units * S.bpu;
-    const unsigned long long vb = img * P.visits_per_image;
-    const unsigned long long bits = b.bitpos[vb + vn] - b.bitpos[vb + vf];
+    const unsigned cps = P.groups[k % P.n_groups].cps;
+    // the segment's chunks are consecutive; the chunk after its last one starts the next segment (or scan, or image)
+    const unsigned long long c0 = img * P.chunks_per_image + S.chunk_base + (unsigned long long)i * cps;
+    const unsigned long long bits = b.chunk_bitpos[c0 + cps] - b.chunk_bitpos[c0];
     const unsigned tail = (s == P.segs_per_image - 1 && P.has_eoi) ? 2u : 0u; // EOI, encoder.rs:564
-    b.seglen[g] = lead_len(b, P, img, k, i) + (unsigned)((bits + 7) >> 3) + tail;
+    const unsigned long long bytes = lead_len(b, P, img, k, i) + ((bits + 7) >> 3) + tail;
+    if (bytes > 0xFFFFFFFFull) atomicOr(b.status + 2, 8ull); // seglen is 32-bit: reported, never wrapped silently
+    b.seglen[g] = (unsigned)bytes;
 }
 
 // Unstuffed stream size as computed on the device; kernels that write the stream bail out (and the
@@ -531,93 +546,61 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
     }
 }
 
-// Moves the already coded bits of visit g from its slot to their place in the unstuffed stream:
-// a bit-granular copy (funnel shift by the start position modulo 32). The first and the last stream
-// word of a visit are shared with its neighbours and are merged with atomicOr (the stream is
-// zero-initialised); words in between are owned and stored. The last visit of a segment also
-// writes the pad bits of finalize_bit_buffer (writer.rs:138-145: ones up to the byte boundary).
-__global__ void __launch_bounds__(256) place_bits_kernel(const EntropyBuffers b, unsigned long long n_visits) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_visits || !stream_fits(b)) return;
+// Streams chunk c from `pool` to its place in the unstuffed stream: a bit-granular copy (funnel shift by the
+// start position modulo 32), one warp per chunk, 128 bytes per step, reads and writes coalesced. The first and the
+// last stream word of a chunk are shared with its neighbours and are merged with atomicOr (the stream is
+// zero-initialised); words in between are owned and stored. The warp of a segment's first chunk also writes the
+// pad bits of finalize_bit_buffer behind the segment's last bit (writer.rs:138-145: ones up to the byte boundary).
+__global__ void __launch_bounds__(256) place_chunks_kernel(const EntropyBuffers b, unsigned long long n_chunks) {
+    if (!stream_fits(b) || (b.status[2] & 4ull)) return;
     const DevPlan &P = *b.plan;
-    // The kernel is bound by the latency of its dependent loads, not by bytes or instructions: the first four slot
-    // words are requested before anything else is known (every visit owns all kSlotWords rows of its tile, so the
-    // loads are always in bounds; words beyond the visit's code are simply not used).
-    const uint32_t *src = slot_of(b.slots, g);
-    uint32_t pre[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pre[q] = src[(size_t)q * kSlotTile];
-    unsigned long long img, v;
-    split_visit(P, g, img, v);
-    unsigned nb = b.nbits[g];
-    // segment bookkeeping only (no coefficient access)
-    bool last_of_seg;
-    unsigned long long data_byte, rel_bits;
-    if (P.n_scans == 1 && P.restart == 0 && P.scans[0].rst_base == 0) {
-        // one scan, no restarts (the interleaved baseline file): the image is one segment that starts with the header
-        last_of_seg = v == P.visits_per_image - 1;
-        if (nb == 0 && !last_of_seg) return;
-        data_byte = b.segpos[img] + b.hdr_len[b.huff_per_image ? img : 0];
-        rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image];
-    } else {
-        const int k = find_scan_by_visit(P, v);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    uint32_t *stream = reinterpret_cast<uint32_t *>(b.ustream);
+    for (unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+        const unsigned long long img = c / P.chunks_per_image;
+        const unsigned r = (unsigned)(c - img * P.chunks_per_image);
+        const int k = find_scan_by_chunk(P, r);
         const DevScan &S = P.scans[k];
-        unsigned unit, slot_in_unit;
-        split_unit(S, v, unit, slot_in_unit);
-        const unsigned R = (unsigned)P.restart;
-        unsigned seg_in_scan = 0, seg_r = unit;
-        if (R) divmod(unit, P.div_restart, seg_in_scan, seg_r);
-        last_of_seg = slot_in_unit == S.bpu - 1 && (unit == S.n_units - 1 || (R && seg_r == R - 1));
-        if (nb == 0 && !last_of_seg) return;
-        const unsigned long long first_visit = S.visit_base + (unsigned long long)seg_in_scan * R * S.bpu;
-        const unsigned long long seg = img * P.segs_per_image + S.seg_base + seg_in_scan;
-        data_byte = b.segpos[seg] + lead_len(b, P, img, k, seg_in_scan);
-        rel_bits = b.bitpos[g] - b.bitpos[img * P.visits_per_image + first_visit];
-    }
-    const unsigned long long bitpos = data_byte * 8 + rel_bits;
-
-    uint32_t *dst = reinterpret_cast<uint32_t *>(b.ustream) + (bitpos >> 5);
-    const unsigned sh = (unsigned)(bitpos & 31);
-    const unsigned n_words = (nb + 31) >> 5;
-    unsigned pad = 0;
-    if (last_of_seg) {
-        const unsigned end_bits = (unsigned)((rel_bits + nb) & 7);
-        pad = end_bits ? 8 - end_bits : 0;
-    }
-    uint32_t carry = 0; // bits still to be written into the current destination word (left-aligned)
-    bool first = true;
-    auto emit = [&](unsigned j, uint32_t w) {
-        const unsigned have = (j + 1 == n_words) ? nb - 32 * j : 32u; // valid bits in w (left-aligned)
-        if (j + 1 == n_words && pad) { // append the pad ones behind the last code bits when they fit in this word
-            if (have + pad <= 32) {
-                w |= ((1u << pad) - 1u) << (32 - have - pad);
-                pad = 0;
+        const DevGroup &G = P.groups[k % P.n_groups];
+        unsigned seg, q;
+        divmod(r - S.chunk_base, G.div_cps, seg, q);
+        const unsigned bits = b.chunk_bits[c];
+        if (bits == 0 && q != 0) continue;
+        const unsigned long long seg_first = b.chunk_bitpos[c - q];
+        const unsigned long long rel_bits = b.chunk_bitpos[c] - seg_first;
+        const unsigned long long data_byte = b.segpos[img * P.segs_per_image + S.seg_base + seg] + lead_len(b, P, img, k, seg);
+        if (q == 0 && lane == 0) { // pad with ones up to the byte boundary behind the segment's last bit
+            const unsigned long long seg_bits = b.chunk_bitpos[c + G.cps] - seg_first;
+            const unsigned pad = (unsigned)(-(long long)seg_bits) & 7u;
+            if (pad) {
+                const unsigned long long pbit = data_byte * 8 + seg_bits;
+                const unsigned s2 = (unsigned)(pbit & 31); // pad never crosses a byte, hence never a word
+                atomicOr(stream + (pbit >> 5), __byte_perm(((1u << pad) - 1u) << (32 - s2 - pad), 0, 0x0123));
             }
         }
-        const uint32_t out = carry | (sh ? (w >> sh) : w);
-        const bool full = sh + have >= 32; // this destination word is completed by w
-        const uint32_t be = __byte_perm(out, 0, 0x0123);
-        if (first || !full) atomicOr(dst, be);
-        else *dst = be;
-        first = false;
-        if (full) {
-            ++dst;
-            carry = sh ? (w << (32 - sh)) : 0u;
-            if (j + 1 == n_words) { // bits of the last word that spilled into the next destination word
-                const unsigned spill = sh + have - 32;
-                if (spill) atomicOr(dst, __byte_perm(carry, 0, 0x0123));
+        if (bits == 0) continue;
+        const unsigned long long bitpos = data_byte * 8 + rel_bits;
+        const unsigned sft = (unsigned)(bitpos & 31);
+        uint32_t *dst = stream + (bitpos >> 5);
+        const uint32_t *src = b.pool + (size_t)b.chunk_pool[c] * 4;
+        const unsigned nw = (bits + 31) >> 5, ndw = (sft + bits + 31) >> 5;
+        const bool first_owned = sft == 0, last_owned = ((sft + bits) & 31) == 0;
+        uint32_t carry = 0; // source word in front of this step's first one
+        for (unsigned base = 0; base < ndw; base += 32) {
+            const unsigned d = base + lane;
+            const uint32_t cur = d < nw ? __ldg(src + d) : 0u;
+            uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+            if (lane == 0) prev = carry;
+            carry = __shfl_sync(0xffffffffu, cur, 31);
+            if (d < ndw) {
+                const uint32_t val = sft ? __funnelshift_r(cur, prev, sft) : cur;
+                const uint32_t be = __byte_perm(val, 0, 0x0123);
+                const bool owned = (d > 0 || first_owned) && (d + 1 < ndw || last_owned);
+                if (owned) dst[d] = be;
+                else atomicOr(dst + d, be);
             }
         }
-    };
-#pragma unroll
-    for (unsigned j = 0; j < 4; ++j)
-        if (j < n_words) emit(j, pre[j]);
-    for (unsigned j = 4; j < n_words; ++j) emit(j, src[(size_t)j * kSlotTile]);
-    if (pad) { // pad bits that did not fit next to the last code word (or a visit without bits)
-        const unsigned long long p = bitpos + nb;
-        uint32_t *d2 = reinterpret_cast<uint32_t *>(b.ustream) + (p >> 5);
-        const unsigned s2 = (unsigned)(p & 31); // pad never crosses a byte, hence never a word
-        atomicOr(d2, __byte_perm(((1u << pad) - 1u) << (32 - s2 - pad), 0, 0x0123));
     }
 }
 
@@ -779,72 +762,61 @@ __global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers 
 }
 
 // ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
-// One thread per block of each component's *true* grid. DC category of the chained difference with
-// no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL
-// for runs > 15, EOB when a band ends in zeros. Bins: [image][table][dc|ac][257].
-__global__ void __launch_bounds__(256) histogram_kernel(const DevPlan *plan, const int16_t *coef, unsigned long long n_blocks_total,
-                                                        unsigned long long blocks_true_per_image, uint32_t *hist,
+// One thread per block; the coefficient buffer holds every component's true grid in raster order (optimized tables
+// always code non-interleaved), so the block in front is the DC predecessor. DC category of the chained difference
+// with no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL for
+// runs > 15, EOB when a band ends in zeros. Bins: [image][table][dc|ac][257]. One launch for the whole batch:
+// blockIdx.y walks the images, a CTA never straddles two of them.
+__global__ void __launch_bounds__(256) histogram_kernel(const DevPlan *plan, const int16_t *coef, unsigned n_images, uint32_t *hist,
                                                         int bands, int per_band) {
     __shared__ unsigned sh[2 * 2 * 257];
-    for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
     const DevPlan &P = *plan;
-    const unsigned long long g0 = (unsigned long long)blockIdx.x * blockDim.x;
-    const unsigned long long g = g0 + threadIdx.x;
-    const unsigned long long img_cta = g0 / blocks_true_per_image; // CTAs never straddle images (grid is per image)
-    if (g < n_blocks_total) {
-        unsigned long long r = g - img_cta * blocks_true_per_image;
-        int comp = 0;
-        for (; comp < P.ncomp - 1; ++comp) {
-            const unsigned long long nb = (unsigned long long)P.comp_tw[comp] * (P.scans[comp].n_units / P.comp_tw[comp]);
-            if (r < nb) break;
-            r -= nb;
-        }
-        const unsigned tw = P.comp_tw[comp], pw = P.comp_pw[comp];
-        const unsigned by = (unsigned)(r / tw), bx = (unsigned)(r - (unsigned long long)by * tw);
-        const int16_t *img_coef = coef + img_cta * P.blocks_per_image * 64;
-        const int16_t *blk = img_coef + (P.comp_off[comp] + (unsigned long long)by * pw + bx) * 64;
-        int prev = 0;
-        if (r > 0) {
-            const unsigned long long pr = r - 1;
-            const unsigned pby = (unsigned)(pr / tw), pbx = (unsigned)(pr - (unsigned long long)pby * tw);
-            prev = img_coef[(P.comp_off[comp] + (unsigned long long)pby * pw + pbx) * 64];
-        }
-        unsigned *h = sh + P.comp_tbl[comp] * 2 * 257;
-        const int diff = (int)(int16_t)(blk[0] - prev);
-        atomicAdd(h + (32 - __clz(diff < 0 ? -diff : diff)), 1u);
-        unsigned *ha = h + 257;
-        const uint4 *src = reinterpret_cast<const uint4 *>(blk);
-        int run = 0, band = 0, band_end = bands == 1 ? 64 : per_band; // band b covers [max(b*per,1), (b+1)*per), last to 64
-        for (int w = 0; w < 8; ++w) {
-            const uint4 q = __ldg(src + w);
-            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; // block inside the image
+    for (unsigned img = blockIdx.y; img < n_images; img += gridDim.y) {
+        for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        if (g < P.blocks_per_image) {
+            int comp = 0;
+            while (comp + 1 < P.n_groups && g >= P.groups[comp + 1].block_base) ++comp;
+            const int16_t *blk = coef + ((unsigned long long)img * P.blocks_per_image + g) * 64;
+            const int prev = g > P.groups[comp].block_base ? (int)blk[-64] : 0;
+            unsigned *h = sh + P.comp_tbl[comp] * 2 * 257;
+            const int diff = (int)(int16_t)(blk[0] - prev);
+            atomicAdd(h + (32 - __clz(diff < 0 ? -diff : diff)), 1u);
+            unsigned *ha = h + 257;
+            const uint4 *src = reinterpret_cast<const uint4 *>(blk);
+            int run = 0, band = 0, band_end = bands == 1 ? 64 : per_band; // band b covers [max(b*per,1), (b+1)*per), last to 64
+            for (int w = 0; w < 8; ++w) {
+                const uint4 q = __ldg(src + w);
+                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = w * 8 + j;
-                if (k == 0) continue;
-                if (k == band_end) { // band boundary: close the previous band
-                    if (run > 0) atomicAdd(ha, 1u);
-                    run = 0;
-                    ++band;
-                    band_end = band == bands - 1 ? 64 : (band + 1) * per_band;
-                }
-                const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
-                if (c == 0) {
-                    ++run;
-                } else {
-                    for (; run > 15; run -= 16) atomicAdd(ha + 0xF0, 1u);
-                    atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
-                    run = 0;
+                for (int j = 0; j < 8; ++j) {
+                    const int k = w * 8 + j;
+                    if (k == 0) continue;
+                    if (k == band_end) { // band boundary: close the previous band
+                        if (run > 0) atomicAdd(ha, 1u);
+                        run = 0;
+                        ++band;
+                        band_end = band == bands - 1 ? 64 : (band + 1) * per_band;
+                    }
+                    const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
+                    if (c == 0) {
+                        ++run;
+                    } else {
+                        for (; run > 15; run -= 16) atomicAdd(ha + 0xF0, 1u);
+                        atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
+                        run = 0;
+                    }
                 }
             }
+            if (run > 0) atomicAdd(ha, 1u);
         }
-        if (run > 0) atomicAdd(ha, 1u);
+        __syncthreads();
+        uint32_t *dst = hist + (size_t)img * (2 * 2 * 257);
+        for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x)
+            if (sh[i]) atomicAdd(dst + i, sh[i]);
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t *dst = hist + img_cta * (2 * 2 * 257);
-    for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x)
-        if (sh[i]) atomicAdd(dst + i, sh[i]);
 }
 
 } // namespace
@@ -853,26 +825,82 @@ static inline unsigned grid_for(unsigned long long n, unsigned block) { return (
 
 cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hp, const int16_t *coef, uint32_t n_images, uint32_t *hist,
                              cudaStream_t stream) {
-    // sequential / progressive plans only: scans 0..ncomp-1 are one per component over its true grid
-    unsigned long long per_image = 0;
-    for (int c = 0; c < hp.ncomp; ++c) per_image += hp.scans[c].n_units;
-    const int bands = hp.n_scans > hp.ncomp ? hp.n_scans / hp.ncomp - 1 : 1;
+    // sequential / progressive plans only (optimized tables never code interleaved)
+    const int bands = hp.spg > 1 ? hp.spg - 1 : 1;
     const int per_band = bands > 1 ? 64 / bands : 64;
-    const unsigned ctas_per_image = grid_for(per_image, 256);
-    // one launch per image keeps CTAs from straddling images; images in a batch are few in optimized mode
-    for (uint32_t i = 0; i < n_images; ++i) {
-        histogram_kernel<<<ctas_per_image, 256, 0, stream>>>(plan, coef + (size_t)i * hp.blocks_per_image * 64, per_image, per_image,
-                                                            hist + (size_t)i * (2 * 2 * 257), bands, per_band);
-    }
+    dim3 grid(grid_for(hp.blocks_per_image, 256), n_images < 32768 ? n_images : 32768);
+    histogram_kernel<<<grid, 256, 0, stream>>>(plan, coef, n_images, hist, bands, per_band);
     return cudaGetLastError();
 }
 
-cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
-    const unsigned long long nv = hp.visits_per_image * n;
-    // progressive plans end with an AC band; in every other mode all scans cover the whole block
-    const bool full = hp.scans[hp.n_scans - 1].ss == 0 && hp.scans[hp.n_scans - 1].se == 63;
-    if (full) encode_visits_kernel<true><<<grid_for(nv, kEncThreads), kEncThreads, 0, s>>>(b, nv);
-    else encode_visits_kernel<false><<<grid_for(nv, kEncThreads), kEncThreads, 0, s>>>(b, nv);
+namespace {
+constexpr int kMaxDevices = 64;
+struct CoderInfo {
+    bool ready = false;
+    int n_sms = 0, ctas_per_sm = 0;
+};
+template <int T, bool FULL>
+cudaError_t coder_info(CoderInfo &out) {
+    static std::mutex mu;
+    static CoderInfo cache[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    CoderInfo &c = cache[dev < kMaxDevices ? dev : kMaxDevices - 1];
+    if (!c.ready) {
+        auto kernel = encode_chunks_kernel<T, FULL>;
+        const int smem = CoderSmem<T, FULL>::kBytes;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.ctas_per_sm, kernel, T, smem);
+        if (e != cudaSuccess) return e;
+        if (c.ctas_per_sm < 1) c.ctas_per_sm = 1;
+        c.ready = true;
+    }
+    out = c;
+    return cudaSuccess;
+}
+template <int T, bool FULL>
+cudaError_t coder_config(unsigned long long n_items, CoderLaunch &cfg) {
+    CoderInfo info;
+    cudaError_t e = coder_info<T, FULL>(info);
+    if (e != cudaSuccess) return e;
+    unsigned long long grid = (unsigned long long)info.n_sms * info.ctas_per_sm;
+    if (grid > n_items) grid = n_items;
+    if (grid < 1) grid = 1;
+    cfg.grid = (unsigned)grid;
+    cfg.smem = CoderSmem<T, FULL>::kBytes;
+    cfg.scratch_bytes = (size_t)grid * T * kSlotWords * 4;
+    return cudaSuccess;
+}
+// progressive plans end with an AC band; in every other mode all scans cover the whole block
+inline bool plan_is_full(const DevPlan &hp) { return hp.scans[hp.n_scans - 1].ss == 0 && hp.scans[hp.n_scans - 1].se == 63; }
+} // namespace
+
+#define JPGB_CODER_DISPATCH(CALL)                              \
+    do {                                                       \
+        const bool full = plan_is_full(hp);                    \
+        switch (hp.chunk_T) {                                  \
+        case 32: if (full) { CALL(32, true); } else { CALL(32, false); } break;    \
+        case 64: if (full) { CALL(64, true); } else { CALL(64, false); } break;    \
+        case 128: if (full) { CALL(128, true); } else { CALL(128, false); } break; \
+        default: if (full) { CALL(256, true); } else { CALL(256, false); } break;  \
+        }                                                      \
+    } while (0)
+
+cudaError_t coder_launch_config(const DevPlan &hp, uint32_t n, CoderLaunch &cfg) {
+    const unsigned long long n_items = (unsigned long long)hp.items_per_image * n;
+#define JPGB_CFG(T, F) return coder_config<T, F>(n_items, cfg)
+    JPGB_CODER_DISPATCH(JPGB_CFG);
+#undef JPGB_CFG
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_encode_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, const CoderLaunch &cfg, cudaStream_t s) {
+    const unsigned long long n_items = (unsigned long long)hp.items_per_image * n;
+#define JPGB_RUN(T, F) encode_chunks_kernel<T, F><<<cfg.grid, T, cfg.smem, s>>>(b, n_items)
+    JPGB_CODER_DISPATCH(JPGB_RUN);
+#undef JPGB_RUN
     return cudaGetLastError();
 }
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
@@ -881,7 +909,9 @@ cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, u
     return cudaGetLastError();
 }
 cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t s) {
-    zero_ustream_kernel<<<148 * 8, 256, 0, s>>>(b, n_segs_total);
+    // sized by the provisioned capacity (the real size is only known on the device): 16 KB per CTA pass
+    const unsigned long long want = (b.ustream_cap + 16383) / 16384;
+    zero_ustream_kernel<<<(unsigned)(want < 4096 ? (want ? want : 1) : 4096), 256, 0, s>>>(b, n_segs_total);
     return cudaGetLastError();
 }
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
@@ -889,9 +919,10 @@ cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uin
     segment_lead_kernel<<<grid_for(ns * 32, 128), 128, 0, s>>>(b, ns);
     return cudaGetLastError();
 }
-cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
-    const unsigned long long nv = hp.visits_per_image * n;
-    place_bits_kernel<<<grid_for(nv, 256), 256, 0, s>>>(b, nv);
+cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    const unsigned long long nc = (unsigned long long)hp.chunks_per_image * n;
+    const unsigned long long ctas = (nc + 7) / 8; // one warp per chunk, grid-stride beyond 64 K CTAs
+    place_chunks_kernel<<<(unsigned)(ctas < 65536 ? (ctas ? ctas : 1) : 65536), 256, 0, s>>>(b, nc);
     return cudaGetLastError();
 }
 cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t s) {

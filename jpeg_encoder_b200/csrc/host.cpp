@@ -296,15 +296,12 @@ int Plan::build(const jpgb_params &params, const jpgb_strip *st) {
     mcu_cols = (p.width + 8 * hmax - 1) / (8 * hmax); // encoder.rs:713-714
     mcu_rows = (p.height + 8 * vmax - 1) / (8 * vmax);
     const uint32_t bw = (p.width + 7) / 8, bh = (p.height + 7) / 8; // encoder.rs:1012-1013
-    blocks_per_image = 0;
     for (int c = 0; c < ncomp; ++c) {
         pad_w[c] = mcu_cols * comps[c].h;
         pad_h[c] = mcu_rows * comps[c].v;
         const uint32_t hs = hmax / comps[c].h, vs = vmax / comps[c].v; // encoder.rs:1021-1025
         true_w[c] = (bw + hs - 1) / hs;
         true_h[c] = (bh + vs - 1) / vs;
-        block_off[c] = blocks_per_image;
-        blocks_per_image += (uint64_t)pad_w[c] * pad_h[c];
     }
     for (int c = ncomp; c < 4; ++c) pad_w[c] = pad_h[c] = true_w[c] = true_h[c] = 0, block_off[c] = 0;
 
@@ -316,6 +313,23 @@ int Plan::build(const jpgb_params &params, const jpgb_strip *st) {
     if (p.progressive_scans) mode = Mode::Progressive;
     else if (p.optimize_huffman || !interleavable) mode = Mode::Sequential;
     else mode = Mode::Interleaved;
+
+    // coefficient layout follows the scan order of the mode, so that a scan reads its blocks linearly
+    blocks_per_image = 0;
+    bpu_interleaved = 0;
+    for (int c = 0; c < ncomp; ++c) {
+        slot_base[c] = bpu_interleaved;
+        bpu_interleaved += comps[c].h * comps[c].v;
+    }
+    if (mode == Mode::Interleaved) {
+        for (int c = 0; c < ncomp; ++c) block_off[c] = 0;
+        blocks_per_image = (uint64_t)mcu_cols * mcu_rows * bpu_interleaved;
+    } else {
+        for (int c = 0; c < ncomp; ++c) {
+            block_off[c] = blocks_per_image;
+            blocks_per_image += (uint64_t)true_w[c] * true_h[c];
+        }
+    }
 
     // scans, with their SOS segments (writer.rs:424-452; Ah/Al always 0)
     scans.clear();
@@ -385,6 +399,48 @@ int Plan::build(const jpgb_params &params, const jpgb_strip *st) {
         segs_per_image += s.n_segs;
     }
 
+    // ---- coding chunks ----
+    n_groups = mode == Mode::Interleaved ? 1 : (uint32_t)ncomp;
+    scans_per_group = (uint32_t)scans.size() / n_groups;
+    uint64_t sv_max = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const Scan &s0 = scans[g];
+        Group &G = groups[g];
+        G.comp = s0.comp;
+        G.bpu = s0.blocks_per_unit;
+        G.n_visits = (uint64_t)s0.n_units * s0.blocks_per_unit;
+        G.block_base = s0.comp < 0 ? 0 : block_off[s0.comp];
+        const uint64_t sv = p.restart_interval ? std::min<uint64_t>((uint64_t)p.restart_interval * G.bpu, G.n_visits) : G.n_visits;
+        G.seg_visits = (uint32_t)(p.restart_interval ? (uint64_t)p.restart_interval * G.bpu : G.n_visits);
+        G.n_segs = s0.n_segs;
+        sv_max = std::max(sv_max, sv);
+    }
+    {   // the largest CTA size whose chunks are filled nearly as well as the best size fills them
+        auto eff = [&](uint32_t T) { return (double)sv_max / (double)((sv_max + T - 1) / T * T); };
+        double best = 0;
+        for (uint32_t T : {256u, 128u, 64u, 32u}) best = std::max(best, eff(T));
+        chunk_T = 32;
+        for (uint32_t T : {256u, 128u, 64u, 32u})
+            if (eff(T) >= 0.8 * best) {
+                chunk_T = T;
+                break;
+            }
+    }
+    items_per_image = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        Group &G = groups[g];
+        const uint64_t sv = std::min<uint64_t>(G.seg_visits, G.n_visits);
+        G.cps = (uint32_t)((sv + chunk_T - 1) / chunk_T);
+        G.item_base = items_per_image;
+        items_per_image += G.n_segs * G.cps;
+    }
+    chunks_per_image = 0;
+    for (size_t k = 0; k < scans.size(); ++k) {
+        const Group &G = groups[k % n_groups];
+        scans[k].chunk_base = chunks_per_image;
+        chunks_per_image += G.n_segs * G.cps;
+    }
+
     // SOI, JFIF APP0, [Adobe APP14], user APPn  (encoder.rs:536-554, writer.rs:216-239)
     prefix.clear();
     put_marker(prefix, 0xD8);
@@ -446,33 +502,43 @@ void Plan::fill_device_plan(DevPlan &d) const {
     d.n_scans = (int)scans.size();
     d.ncomp = ncomp;
     d.restart = p.restart_interval;
+    d.n_groups = (int)n_groups;
+    d.spg = (int)scans_per_group;
+    d.chunk_T = (int)chunk_T;
+    d.mcu_order = mode == Mode::Interleaved;
     d.mcu_cols = mcu_cols;
-    d.visits_per_image = visits_per_image;
     d.blocks_per_image = blocks_per_image;
     d.segs_per_image = segs_per_image;
+    d.chunks_per_image = chunks_per_image;
+    d.items_per_image = items_per_image;
     d.has_eoi = !is_strip || strip.strip_index + 1 == strip.n_strips;
-    d.div_mcu_cols = make_fastdiv(mcu_cols);
-    d.div_restart = make_fastdiv(p.restart_interval);
-    d.div_vpi = make_fastdiv(visits_per_image >> 32 ? 0u : (unsigned)visits_per_image);
-    if (visits_per_image >> 32) d.div_vpi.d = 0;
     int n = 0;
     for (int c = 0; c < ncomp; ++c) {
-        d.comp_h[c] = comps[c].h;
-        d.comp_v[c] = comps[c].v;
         d.comp_tbl[c] = comps[c].dc_table;
-        d.comp_pw[c] = pad_w[c];
-        d.comp_tw[c] = true_w[c];
-        d.div_tw[c] = make_fastdiv(true_w[c]);
-        d.comp_off[c] = block_off[c];
-        for (int v = 0; v < comps[c].v; ++v)   // MCU order: component, then v outer, h inner (encoder.rs:759-761)
-            for (int h = 0; h < comps[c].h; ++h) {
-                d.slot_comp[n] = (int8_t)c;
-                d.slot_v[n] = (int8_t)v;
-                d.slot_h[n] = (int8_t)h;
-                ++n;
-            }
+        const int per_mcu = comps[c].h * comps[c].v;
+        for (int i = 0; i < per_mcu; ++i) { // MCU order: component, then v outer, h inner (encoder.rs:759-761)
+            d.slot_comp[n] = (int8_t)c;
+            d.slot_first[n] = i == 0;
+            // the DC predecessor is the previous block of the component: the slot before, or the component's last slot of the MCU before
+            d.slot_back[n] = (uint8_t)(i == 0 ? bpu_interleaved - (per_mcu - 1) : 1);
+            ++n;
+        }
     }
     d.n_slots = n;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const Group &G = groups[g];
+        DevGroup &D = d.groups[g];
+        D.comp = G.comp;
+        D.bpu = G.bpu;
+        D.n_visits = G.n_visits;
+        D.block_base = G.block_base;
+        D.seg_visits = G.seg_visits;
+        D.n_segs = G.n_segs;
+        D.cps = G.cps;
+        D.item_base = G.item_base;
+        D.div_cps = make_fastdiv(G.cps);
+        D.div_bpu = make_fastdiv(G.bpu);
+    }
     unsigned blob = 0;
     for (size_t k = 0; k < scans.size(); ++k) {
         const Scan &s = scans[k];
@@ -482,10 +548,9 @@ void Plan::fill_device_plan(DevPlan &d) const {
         ds.se = s.se;
         ds.n_units = s.n_units;
         ds.bpu = s.blocks_per_unit;
-        ds.div_bpu = make_fastdiv(s.blocks_per_unit);
-        ds.visit_base = s.visit_base;
         ds.seg_base = s.seg_base;
         ds.n_segs = s.n_segs;
+        ds.chunk_base = s.chunk_base;
         ds.rst_base = s.rst_base;
         ds.sos_off = blob;
         ds.sos_len = 0;
@@ -511,6 +576,8 @@ void Plan::fill_stage_a(StageAParams &a) const {
     a.vmax = vmax;
     a.mcu_cols = (int)mcu_cols;
     a.mcu_rows = (int)mcu_rows;
+    a.mcu_order = mode == Mode::Interleaved;
+    a.bpu = (int)bpu_interleaved;
     int n = 0;
     for (int c = 0; c < ncomp; ++c) {
         a.comp_h[c] = comps[c].h;
@@ -518,6 +585,9 @@ void Plan::fill_stage_a(StageAParams &a) const {
         a.comp_qt[c] = comps[c].qtable;
         a.comp_pw[c] = (int)pad_w[c];
         a.comp_off[c] = block_off[c];
+        a.comp_tw[c] = (int)true_w[c];
+        a.comp_th[c] = (int)true_h[c];
+        a.slot_base[c] = (int)slot_base[c];
         for (int v = 0; v < comps[c].v; ++v)
             for (int h = 0; h < comps[c].h; ++h) {
                 a.task_comp[n] = (int8_t)c;

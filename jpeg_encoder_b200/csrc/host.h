@@ -48,6 +48,7 @@ struct Scan {
     uint32_t n_units, blocks_per_unit;
     uint64_t visit_base;   // first block visit of this scan inside one image
     uint32_t seg_base, n_segs;
+    uint32_t chunk_base = 0; // first coding chunk of this scan inside one image
     uint32_t rst_base = 0; // restart segments of this scan before this strip
     std::vector<uint8_t> sos; // SOS segment bytes (marker included)
 };
@@ -61,7 +62,20 @@ struct Plan {
     uint32_t mcu_cols, mcu_rows;
     uint32_t pad_w[4], pad_h[4];   // MCU-padded block grid per component
     uint32_t true_w[4], true_h[4]; // grid walked by encode_blocks (src/encoder.rs:1012-1025)
+    // Coefficient buffer of one image. Interleaved mode: blocks in MCU order (block = mcu * bpu + slot),
+    // block_off unused. Other modes: per component the raster of its true grid, components back to back at block_off[c].
     uint64_t block_off[4], blocks_per_image;
+    uint32_t bpu_interleaved = 0;   // blocks per MCU
+    uint32_t slot_base[4] = {};     // first slot of component c inside the MCU
+    // Coding chunks: a chunk is <= chunk_T consecutive visits of one restart segment of one scan; scans that walk the
+    // same blocks (a component's DC scan and AC bands) form a group whose chunks are coded by the same CTA.
+    uint32_t chunk_T = 256, n_groups = 1, scans_per_group = 1;
+    struct Group {
+        int comp;
+        uint32_t bpu, seg_visits, n_segs, cps, item_base;
+        uint64_t n_visits, block_base;
+    } groups[4];
+    uint32_t chunks_per_image = 0, items_per_image = 0;
     QuantTable q[2];
     Mode mode;
     std::vector<Scan> scans;

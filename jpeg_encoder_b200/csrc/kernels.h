@@ -21,9 +21,13 @@ struct EntropyBuffers {
     const int16_t *coef;           // n * blocks_per_image * 64
     const uint32_t *huff;          // n_huff * kHuffWordsPerImage; n_huff is 1 (shared) or n (optimized)
     int huff_per_image;            // 0: all images share tables[0]; 1: one set per image
-    uint32_t *nbits;               // n * visits_per_image
-    uint32_t *slots;               // kSlotWords words per visit, tiled by kSlotTile visits (entropy.cu: slot_of)
-    unsigned long long *bitpos;    // n * visits_per_image + 1   (exclusive scan of nbits)
+    // coding: one chunk = the code bits of <= chunk_T consecutive visits of one restart segment of one scan
+    uint32_t *scratch;             // per coding CTA: chunk_T visits x kSlotWords words (lives in L2)
+    uint32_t *pool;                // chunk bit strings, MSB-first 32-bit words, each chunk 16-byte aligned, in completion order
+    unsigned long long pool_cap;   // capacity of `pool` in 16-byte units
+    uint32_t *chunk_bits;          // n * chunks_per_image: code bits of the chunk
+    uint32_t *chunk_pool;          // n * chunks_per_image: where the chunk lies in `pool`, in 16-byte units
+    unsigned long long *chunk_bitpos; // n * chunks_per_image + 1 (exclusive scan of chunk_bits)
     uint32_t *seglen;              // n * segs_per_image          (lead + data + tail bytes of a segment)
     unsigned long long *segpos;    // n * segs_per_image + 1      (exclusive scan of seglen)
     const uint32_t *hdr_len;       // n_huff entries: bytes of file header (SOI .. first SOS)
@@ -39,23 +43,31 @@ struct EntropyBuffers {
     // capacities (bytes) of ustream / out and the status block the kernels report into: the host sizes the
     // buffers from the previous call and checks `status` once at the end instead of syncing mid-pipeline
     unsigned long long ustream_cap, out_cap, n_segs_total;
-    unsigned long long *status;    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out), [3] scan error
+    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out, 4: pool, 8: a segment over 4 GiB),
+    // [3] scan error, [4] work-item ticket of the coding kernel, [5] pool cursor (16-byte units)
+    unsigned long long *status;
     size_t scan_tmp_bytes;
 };
+constexpr int kStatusWords = 8;
 
 // A visit codes at most 1 + 63 symbols of <= 16 code + 11 value bits = 1728 bits = 54 words.
 constexpr int kSlotWords = 56;
-constexpr int kSlotTile = 256;  // visits per slot tile = threads of the coding CTA
 constexpr int kStuffChunk = 4096; // bytes of unstuffed stream per CTA in the stuffing kernels
 
 // entropy.cu
 cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hplan, const int16_t *coef, uint32_t n_images,
                              uint32_t *hist /* n * 2 tables * 2 classes * 257 */, cudaStream_t stream);
-cudaError_t launch_symbol_sizes(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+// persistent coding kernel: grid = what coder_grid() returns for this plan; `b.scratch` holds coder_scratch_bytes()
+struct CoderLaunch {
+    unsigned grid;
+    size_t smem, scratch_bytes;
+};
+cudaError_t coder_launch_config(const DevPlan &hplan, uint32_t n_images, CoderLaunch &cfg);
+cudaError_t launch_encode_chunks(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, const CoderLaunch &cfg, cudaStream_t stream);
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t stream);
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
-cudaError_t launch_emit_bits(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t stream);   // grids sized by b.ustream_cap
 cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t stream);
 cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, unsigned long long *offs,

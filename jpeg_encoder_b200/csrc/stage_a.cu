@@ -197,8 +197,14 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
         for (int x = 0; x < 8; ++x)
             dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
 
-        const size_t blk = (size_t)img * p.blocks_per_image + p.comp_off[comp] +
-                           (size_t)(mcu_y * p.comp_v[comp] + bv) * p.comp_pw[comp] + (size_t)mcu_x * p.comp_h[comp] + bh;
+        size_t blk = (size_t)img * p.blocks_per_image;
+        if (p.mcu_order) { // the order the interleaved scan codes them (encoder.rs:747-791)
+            blk += ((size_t)mcu_y * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * p.comp_h[comp] + bh;
+        } else {           // raster of the component's true grid (encoder.rs:1012-1031); MCU padding blocks are not stored
+            const int by = mcu_y * p.comp_v[comp] + bv, bx = mcu_x * p.comp_h[comp] + bh;
+            if (bx >= p.comp_tw[comp] || by >= p.comp_th[comp]) continue;
+            blk += p.comp_off[comp] + (size_t)by * p.comp_tw[comp] + bx;
+        }
         int16_t *dst = p.coef + blk * 64;
         if (p.comp_qt[comp] == 0) quantize_store<0>(p, v, dst);
         else quantize_store<1>(p, v, dst);
@@ -594,7 +600,8 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             }
             const int H = full ? HS : 1, V = full ? VS : 1;
             const int bx = mcu_x0 * H + bxl;
-            if (bx >= p.comp_pw[comp]) continue;
+            // blocks of the MCU padding exist only in the MCU-ordered layout (the interleaved scan codes them)
+            if (p.mcu_order ? bx >= p.comp_pw[comp] : (bx >= p.comp_tw[comp] || mcu_y * V + bv >= p.comp_th[comp])) continue;
             const uint8_t *base = full ? mtile + (bv * 8) * PITCH + bxl * 8 * BPP : mtile + bxl * 8 * HS * BPP;
 
             int v[64];
@@ -617,7 +624,13 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             for (int x = 0; x < 8; ++x)
                 dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
 
-            const size_t blk = (size_t)img * p.blocks_per_image + p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_pw[comp] + bx;
+            size_t blk = (size_t)img * p.blocks_per_image;
+            if (p.mcu_order) { // H, V are 1 or 2 here: bx = mcu_x * H + bh
+                const int mcu_x = H == 2 ? bx >> 1 : bx, bh = H == 2 ? bx & 1 : 0;
+                blk += ((size_t)mcu_y * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * H + bh;
+            } else {
+                blk += p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_tw[comp] + bx;
+            }
             int16_t *dst = p.coef + blk * 64;
             if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
             else quantize_store256<1>(p, v, dst);

@@ -147,7 +147,8 @@ class _Params(C.Structure):
 class _CoefLayout(C.Structure):
     _fields_ = [("n_components", C.c_uint32), ("blocks_w", C.c_uint32 * 4), ("blocks_h", C.c_uint32 * 4),
                 ("true_w", C.c_uint32 * 4), ("true_h", C.c_uint32 * 4), ("block_offset", C.c_uint64 * 4),
-                ("blocks_per_image", C.c_uint64)]
+                ("blocks_per_image", C.c_uint64), ("mcu_order", C.c_uint32), ("mcu_cols", C.c_uint32), ("mcu_rows", C.c_uint32),
+                ("blocks_per_mcu", C.c_uint32), ("slot_base", C.c_uint32 * 4), ("comp_h", C.c_uint32 * 4), ("comp_v", C.c_uint32 * 4)]
 
 
 class _Strip(C.Structure):
@@ -157,7 +158,7 @@ class _Strip(C.Structure):
 
 N_STAGES = 7
 HIST_WORDS = 2 * 2 * 257  # JPGB_HIST_WORDS
-STAGE_NAMES = ("colour_dct_quant", "histogram_tables", "symbol_sizes_scans", "emit_bits", "stuff_scatter", "h2d", "d2h")
+STAGE_NAMES = ("colour_dct_quant", "histogram_tables", "code_chunks_scans", "place_chunks", "stuff_scatter", "h2d", "d2h")
 
 _lib = None
 

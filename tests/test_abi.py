@@ -68,13 +68,19 @@ def test_coef_layout_matches_reference_block_counts():
     e.set_sampling_factor(je.SamplingFactor.F_2_2)
     lay = e.coef_layout(1920, 1080, je.ColorType.Rgb)
     assert [lay.blocks_w[c] * lay.blocks_h[c] for c in range(3)] == [32640, 8160, 8160]
-    assert lay.blocks_per_image == 48960
+    assert lay.blocks_per_image == 48960 and lay.mcu_order == 1 and lay.blocks_per_mcu == 6  # interleaved: MCU order, padding included
     assert (lay.true_w[0], lay.true_h[0], lay.true_w[1], lay.true_h[1]) == (240, 135, 120, 68)
     lay = e.coef_layout(4096, 4096, je.ColorType.Rgb)
     assert lay.blocks_per_image == 512 * 512 + 2 * 256 * 256
     e.set_sampling_factor(je.SamplingFactor.F_4_1)
     lay = e.coef_layout(258, 128, je.ColorType.Rgb)  # 9 MCU columns of 32 px
     assert (lay.blocks_w[0], lay.blocks_h[0], lay.true_w[0], lay.true_w[1]) == (36, 16, 33, 9)
+    e = je.Encoder(90)
+    e.set_sampling_factor(je.SamplingFactor.F_2_2)
+    e.set_optimized_huffman_tables(True)  # sequential: the true grids encode_blocks walks, raster order, no padding blocks
+    lay = e.coef_layout(1920, 1080, je.ColorType.Rgb)
+    assert lay.mcu_order == 0 and lay.blocks_per_image == 240 * 135 + 2 * 120 * 68
+    assert list(lay.block_offset)[:3] == [0, 240 * 135, 240 * 135 + 120 * 68]
     lay = je.Encoder(95).coef_layout(8192, 8192, je.ColorType.CmykAsYcck)
     assert lay.n_components == 4 and lay.blocks_per_image == 4 * 1024 * 1024
 

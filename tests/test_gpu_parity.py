@@ -42,14 +42,15 @@ def test_committed_file_hashes():
 
 
 # ---- stage A on its own: coefficients bit-exact --------------------------------------------------
+@pytest.mark.parametrize("optimize", [False, True])  # interleaved (MCU-ordered buffer) / sequential (raster of the true grids)
 @pytest.mark.parametrize("color,sampling", [("rgb", (2, 2)), ("rgb", (1, 1)), ("rgb", (4, 1)), ("rgb", (2, 4)), ("luma", (1, 1)),
                                             ("cmyk_as_ycck", (1, 1)), ("cmyk", (2, 2)), ("bgra", (2, 1)), ("ycck", (1, 2))])
-def test_stage_a_coefficients(color, sampling):
+def test_stage_a_coefficients(color, sampling, optimize):
     import torch
     import jpeg_encoder_b200 as je
     w, h = 203, 131
     img = _img(color, w, h)
-    cfg = dict(quality=85, sampling=sampling)
+    cfg = dict(quality=85, sampling=sampling, optimize_huffman=optimize)
     enc = make_encoder(cfg)
     lay = enc.coef_layout(w, h, CT[color][1])
     d_px = torch.from_numpy(img.reshape(-1).copy()).cuda()
@@ -62,10 +63,22 @@ def test_stage_a_coefficients(color, sampling):
     torch.cuda.synchronize()
     got = d_coef.cpu().numpy().reshape(-1, 64)
     want = orc.coefficients(img, w, h, CT[color][0], **cfg)
+    seen = np.zeros(lay.blocks_per_image, bool)
     for c in range(lay.n_components):
-        o, n = lay.block_offset[c], lay.blocks_w[c] * lay.blocks_h[c]
-        assert n == want[c].shape[0]
-        np.testing.assert_array_equal(got[o:o + n], want[c], err_msg="component %d" % c)
+        pw, ph = lay.blocks_w[c], lay.blocks_h[c]
+        assert pw * ph == want[c].shape[0]  # the oracle holds the MCU-padded grid of every component, raster order
+        by, bx = np.divmod(np.arange(pw * ph), pw)
+        if lay.mcu_order:  # interleaved scan: blocks in coding order (include/jpegenc_b200.h, jpgb_coef_layout)
+            H, V = lay.comp_h[c], lay.comp_v[c]
+            idx = ((by // V) * lay.mcu_cols + bx // H) * lay.blocks_per_mcu + lay.slot_base[c] + (by % V) * H + bx % H
+            keep = np.ones(pw * ph, bool)
+        else:              # raster of the true grid; MCU padding blocks are not stored
+            keep = (by < lay.true_h[c]) & (bx < lay.true_w[c])
+            idx = lay.block_offset[c] + by * lay.true_w[c] + bx
+        np.testing.assert_array_equal(got[idx[keep]], want[c][keep], err_msg="component %d" % c)
+        assert not seen[idx[keep]].any()
+        seen[idx[keep]] = True
+    assert seen.all(), "every block of the buffer belongs to exactly one component position"
 
 
 def test_generic_and_fast_stage_a_kernels_agree(monkeypatch):
