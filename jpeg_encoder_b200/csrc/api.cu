@@ -70,9 +70,9 @@ struct jpgb_encoder {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    DevBuf pixels, coef, plan, huff, hdr, hdr_len, scratch, pool, chunk_bits, chunk_pool, chunk_bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos,
+    DevBuf pixels, coef, huff, hdr, hdr_len, scratch, pool, chunk_bits, chunk_pool, chunk_bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos,
         out, file_off, scan_tmp, hist, piece_off, out2, pixels2, status, scan_err;
-    std::vector<uint8_t> last_plan, last_tables; // what the device currently holds
+    std::vector<uint8_t> last_tables; // what the device currently holds
     double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
     double pool_ratio = 0; // the same for the chunk pool (code bytes incl. per-chunk alignment)
     PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out, h_stage[2];
@@ -168,14 +168,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     const uint64_t n_segs = (uint64_t)plan.segs_per_image * n;
 
     CK(enc->coef.reserve(n_blocks * 128), "alloc coefficients");
-    CK(enc->plan.reserve(sizeof(DevPlan)), "alloc plan");
-    // repeated calls with the same settings skip the small uploads (the device copies are still valid)
-    if (enc->last_plan.size() != sizeof(DevPlan) || std::memcmp(enc->last_plan.data(), &hp, sizeof(DevPlan)) != 0) {
-        enc->last_plan.assign(reinterpret_cast<const uint8_t *>(&hp), reinterpret_cast<const uint8_t *>(&hp) + sizeof(DevPlan));
-        CK(cudaMemcpyAsync(enc->plan.p, enc->last_plan.data(), sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
-        CK(cudaStreamSynchronize(st), "plan upload sync"); // pageable source: keep it simple and rare
-    }
-
     // ---- stage A ----
     {
         StageTimer t(enc, 0);
@@ -200,7 +192,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         } else {
             CK(enc->hist.reserve(hist_words * 4), "alloc histogram");
             CK(cudaMemsetAsync(enc->hist.p, 0, hist_words * 4, st), "clear histogram");
-            CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
+            CK(launch_histogram(hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
             enc->launches += 1;
             CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_words * 4, cudaMemcpyDeviceToHost, st), "download histogram");
             CK(cudaStreamSynchronize(st), "histogram sync");
@@ -265,7 +257,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     CK(enc->scratch.reserve(coder.scratch_bytes), "alloc coder scratch");
 
     EntropyBuffers b{};
-    b.plan = enc->plan.as<DevPlan>();
     b.coef = enc->coef.as<int16_t>();
     b.huff = enc->huff.as<uint32_t>();
     b.huff_per_image = optimized ? 1 : 0;
@@ -581,7 +572,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->plan, &e->huff, &e->hdr, &e->hdr_len, &e->scratch, &e->pool, &e->chunk_bits, &e->chunk_pool, &e->chunk_bitpos, &e->seglen, &e->segpos,
+    DevBuf *bufs[] = {&e->pixels, &e->coef, &e->huff, &e->hdr, &e->hdr_len, &e->scratch, &e->pool, &e->chunk_bits, &e->chunk_pool, &e->chunk_bitpos, &e->seglen, &e->segpos,
                       &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status, &e->scan_err};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
@@ -812,12 +803,6 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     StageAParams ap;
     plan.fill_stage_a(ap);
     CK(enc->coef.reserve(plan.blocks_per_image * 128), "alloc coefficients");
-    CK(enc->plan.reserve(sizeof(DevPlan)), "alloc plan");
-    if (enc->last_plan.size() != sizeof(DevPlan) || std::memcmp(enc->last_plan.data(), &hp, sizeof(DevPlan)) != 0) {
-        enc->last_plan.assign(reinterpret_cast<const uint8_t *>(&hp), reinterpret_cast<const uint8_t *>(&hp) + sizeof(DevPlan));
-        CK(cudaMemcpyAsync(enc->plan.p, enc->last_plan.data(), sizeof(DevPlan), cudaMemcpyHostToDevice, st), "upload plan");
-        CK(cudaStreamSynchronize(st), "plan upload sync");
-    }
     ap.pixels = static_cast<const uint8_t *>(d_pixels);
     ap.coef = enc->coef.as<int16_t>();
     ap.image_stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
@@ -826,7 +811,7 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     CK(enc->hist.reserve(hist_bytes), "alloc histogram");
     CK(enc->h_hist.reserve(hist_bytes + 16), "alloc histogram (host)");
     CK(cudaMemsetAsync(enc->hist.p, 0, hist_bytes, st), "clear histogram");
-    CK(launch_histogram(enc->plan.as<DevPlan>(), hp, enc->coef.as<int16_t>(), 1, enc->hist.as<uint32_t>(), st), "histogram launch");
+    CK(launch_histogram(hp, enc->coef.as<int16_t>(), 1, enc->hist.as<uint32_t>(), st), "histogram launch");
     enc->launches = 2;
     CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_bytes, cudaMemcpyDeviceToHost, st), "download histogram");
     // DC of the first and of the last block of every component's true grid (the histogram chains DC differences

@@ -98,6 +98,7 @@ struct DevPlan {
     unsigned mcu_cols;
     unsigned long long blocks_per_image;
     unsigned segs_per_image, chunks_per_image, items_per_image;
+    FastDiv div_items;      // by items_per_image (tickets below 2^32; beyond that the kernel divides in 64 bits)
     int has_eoi;            // 0 for every strip but the last
     int8_t slot_comp[kMaxSlots];
     uint8_t slot_back[kMaxSlots];   // interleaved: distance (in blocks of the MCU-ordered buffer) to the DC predecessor

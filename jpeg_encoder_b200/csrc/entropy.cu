@@ -132,7 +132,7 @@ __device__ __forceinline__ unsigned long long zrl_markers(unsigned long long m, 
 // coefficient, or a ZRL marker (zrl_markers): a zero 15 positions after the start of its run, for which the same
 // arithmetic yields the symbol 0xF0 with no value bits (writer.rs:369-373), so the loop has no ZRL branch.
 template <int BASE, int T>
-__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint32_t *__restrict__ tab, BitSink<T> &sink) {
+__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint2 *__restrict__ tab, BitSink<T> &sink) {
 #pragma unroll 1
     while (m) {
         int p;
@@ -148,20 +148,20 @@ __device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shar
         int size;
         uint32_t bits;
         value_code(v, size, bits);
-        const uint32_t e = (tab + run * 16)[size];
-        sink.put((e & kCodeBits) | bits, (int)(e >> 27));
+        const uint2 e = (tab + run * 16)[size]; // .x = code << size, .y = code length + size
+        sink.put(e.x | bits, (int)e.y);
     }
 }
 template <int T>
 __device__ __forceinline__ void code_nonzeros(unsigned lo_rev, unsigned hi_rev, int first_ac, int se, const int16_t *__restrict__ c,
-                                              const uint32_t *__restrict__ tab, BitSink<T> &sink) {
+                                              const uint2 *__restrict__ tab, BitSink<T> &sink) {
     int next = first_ac;
     const unsigned c_shared = (unsigned)__cvta_generic_to_shared(c);
     code_half<0, T>(lo_rev, next, c_shared, tab, sink);
     code_half<32, T>(hi_rev, next, c_shared, tab, sink);
     if (next <= se) { // the band ends in zeros: EOB (writer.rs:383-385)
-        const uint32_t e = tab[0];
-        sink.put(e & kCodeBits, (int)(e >> 27));
+        const uint2 e = tab[0];
+        sink.put(e.x, (int)e.y);
     }
 }
 
@@ -180,15 +180,16 @@ struct CoderSmem {
     static constexpr int oAsm = FULL ? 0 : kCoefBytes;
     static constexpr int oMask = kCoefBytes + (FULL ? 0 : kAsmWordsProg * 4);
     static constexpr int oAc = oMask + T * 8;
-    static constexpr int oDc = oAc + 2048;
-    static constexpr int oBin = oDc + 128;
+    static constexpr int oDc = oAc + 4096;  // AC tables: 2 x 256 x {code << size, length}
+    static constexpr int oSlot = oDc + 256; // DC tables: 2 x 16 x {code << size, length}
+    static constexpr int oBin = oSlot + 128; // per MCU slot: table | distance to the DC predecessor << 8 | first of its component << 16
     static constexpr int oNb = oBin + 256;
     static constexpr int oFirst = oNb + T * 4;
     static constexpr int oInfo = oFirst + T * 4;
     static constexpr int oOrder = oInfo + T * 4;
     static constexpr int oWsum = oOrder + T * 2;
     static constexpr int oItem = oWsum + 64;
-    static constexpr int kBytes = oItem + 64;
+    static constexpr int kBytes = oItem + 2 * 64; // two ItemInfo: the chunk being coded and the next one
 };
 
 // write_dc + write_ac_block for one chunk after the other (persistent CTAs, a ticket per chunk):
@@ -203,59 +204,75 @@ struct CoderSmem {
 //     chunk's bit string, assembled in shared memory and written to `pool` with coalesced 128-bit stores.
 // FULL: every scan of the plan covers the whole block (baseline and sequential modes).
 template <int T, bool FULL>
-__global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b, unsigned long long n_items) {
+__global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P,
+                                                          unsigned long long n_items) {
     using L = CoderSmem<T, FULL>;
     extern __shared__ __align__(16) unsigned char smem[];
     int16_t *coef = reinterpret_cast<int16_t *>(smem);
     uint32_t *asmbuf = reinterpret_cast<uint32_t *>(smem + L::oAsm);
     unsigned long long *maskv = reinterpret_cast<unsigned long long *>(smem + L::oMask);
-    uint32_t *ac_tab = reinterpret_cast<uint32_t *>(smem + L::oAc);
-    uint32_t *dc_tab = reinterpret_cast<uint32_t *>(smem + L::oDc);
+    uint2 *ac_tab = reinterpret_cast<uint2 *>(smem + L::oAc);
+    uint2 *dc_tab = reinterpret_cast<uint2 *>(smem + L::oDc);
+    uint32_t *slot_tab = reinterpret_cast<uint32_t *>(smem + L::oSlot);
     uint32_t *bin = reinterpret_cast<uint32_t *>(smem + L::oBin);
     uint32_t *nbv = reinterpret_cast<uint32_t *>(smem + L::oNb);
     uint32_t *firstv = reinterpret_cast<uint32_t *>(smem + L::oFirst);
     uint32_t *infov = reinterpret_cast<uint32_t *>(smem + L::oInfo);
     uint16_t *order = reinterpret_cast<uint16_t *>(smem + L::oOrder);
     uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + L::oWsum); // [0..7] warp sums, [8] pool offset of the chunk
-    ItemInfo *item = reinterpret_cast<ItemInfo *>(smem + L::oItem);
+    ItemInfo *items = reinterpret_cast<ItemInfo *>(smem + L::oItem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevPlan &P = *b.plan;
     uint32_t *scratch = b.scratch + (size_t)blockIdx.x * (T * kSlotWords);
     long long tab_img = -1; // whose Huffman tables the shared copy holds
     for (int i = tid; i < 64; i += T) bin[i] = 0;
-
-    for (;;) {
-        __syncthreads(); // the previous chunk is completely written out
-        if (tid == 0) {
-            const unsigned long long it = atomicAdd(b.status + 4, 1ull);
-            ItemInfo ii{};
-            ii.done = it >= n_items;
-            if (!ii.done) {
-                const unsigned long long img = it / P.items_per_image;
-                unsigned r = (unsigned)(it - img * P.items_per_image);
-                int g = 0;
-                while (g + 1 < P.n_groups && r >= P.groups[g + 1].item_base) ++g;
-                const DevGroup &G = P.groups[g];
-                r -= G.item_base;
-                unsigned seg, chunk;
-                divmod(r, G.div_cps, seg, chunk);
-                const unsigned long long seg_start = (unsigned long long)seg * G.seg_visits;
-                const unsigned long long v0 = seg_start + (unsigned long long)chunk * T;
-                unsigned long long seg_end = seg_start + G.seg_visits;
-                if (seg_end > G.n_visits) seg_end = G.n_visits;
-                ii.img = img;
-                ii.group = (unsigned)g;
-                ii.v_in_seg0 = chunk * T;
-                ii.n_valid = v0 < seg_end ? (unsigned)(seg_end - v0 < (unsigned long long)T ? seg_end - v0 : T) : 0u;
-                ii.blk0 = img * P.blocks_per_image + G.block_base + v0;
-                ii.chunk_index0 = img * P.chunks_per_image + r;
-            }
-            *item = ii;
+    if (tid < kMaxSlots) slot_tab[tid] = (unsigned)P.comp_tbl[P.slot_comp[tid]] | (unsigned)P.slot_back[tid] << 8 | (unsigned)P.slot_first[tid] << 16;
+    // Work items are handed out by a ticket counter. Thread 0 runs one chunk ahead: while the CTA codes chunk i it
+    // requests the ticket of chunk i + 2 and works out where chunk i + 1 lies, so neither the round trip of the
+    // atomic nor the arithmetic is ever waited for.
+    auto decode = [&](unsigned long long ticket, ItemInfo &it) {
+        it.done = ticket >= n_items;
+        if (it.done) return;
+        unsigned long long img;
+        unsigned r;
+        if ((ticket >> 32) == 0) {
+            unsigned q;
+            divmod((unsigned)ticket, P.div_items, q, r);
+            img = q;
+        } else {
+            img = ticket / P.items_per_image;
+            r = (unsigned)(ticket - img * P.items_per_image);
         }
-        __syncthreads();
-        const ItemInfo it = *item;
+        int g = 0;
+        while (g + 1 < P.n_groups && r >= P.groups[g + 1].item_base) ++g;
+        const DevGroup &G = P.groups[g];
+        unsigned seg, chunk;
+        divmod(r - G.item_base, G.div_cps, seg, chunk);
+        const unsigned long long seg_start = (unsigned long long)seg * G.seg_visits;
+        const unsigned long long v0 = seg_start + (unsigned long long)chunk * T;
+        unsigned long long seg_end = seg_start + G.seg_visits;
+        if (seg_end > G.n_visits) seg_end = G.n_visits;
+        it.img = img;
+        it.group = (unsigned)g;
+        it.v_in_seg0 = chunk * T;
+        it.n_valid = v0 < seg_end ? (unsigned)(seg_end - v0 < (unsigned long long)T ? seg_end - v0 : T) : 0u;
+        it.blk0 = img * P.blocks_per_image + G.block_base + v0;
+        it.chunk_index0 = img * P.chunks_per_image + (r - G.item_base);
+    };
+    unsigned long long next_ticket = 0;
+    if (tid == 0) {
+        decode(atomicAdd(b.status + 4, 1ull), items[0]);
+        next_ticket = atomicAdd(b.status + 4, 1ull);
+    }
+
+    for (unsigned round = 0;; ++round) {
+        __syncthreads(); // the previous chunk is completely written out; items[round & 1] is ready
+        const ItemInfo it = items[round & 1];
         if (it.done) break;
+        if (tid == 0) {
+            decode(next_ticket, items[(round & 1) ^ 1]);
+            next_ticket = atomicAdd(b.status + 4, 1ull);
+        }
         if (it.n_valid == 0) { // a chunk slot past the end of a short last segment: it exists only as an (empty) descriptor
             for (int j = tid; j < P.spg; j += T) {
                 const unsigned long long ci = it.chunk_index0 + P.scans[it.group + j * P.n_groups].chunk_base;
@@ -271,8 +288,14 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b
         const long long want_tab = b.huff_per_image ? (long long)it.img : 0;
         if (want_tab != tab_img) {
             const uint32_t *set = b.huff + (size_t)want_tab * kHuffWordsPerImage;
-            for (int i = tid; i < 512; i += T) ac_tab[i] = __ldg(set + (i >> 8) * 512 + 256 + (i & 255)); // table 0 / 1, AC
-            if (tid < 32) dc_tab[tid] = __ldg(set + (tid >> 4) * 512 + (tid & 15));                        // DC categories 0..15
+            for (int i = tid; i < 512; i += T) { // table 0 / 1, AC
+                const uint32_t e = __ldg(set + (i >> 8) * 512 + 256 + (i & 255));
+                ac_tab[i] = make_uint2(e & kCodeBits, e >> 27);
+            }
+            if (tid < 32) { // DC categories 0..15
+                const uint32_t e = __ldg(set + (tid >> 4) * 512 + (tid & 15));
+                dc_tab[tid] = make_uint2(e & kCodeBits, e >> 27);
+            }
             tab_img = want_tab;
         }
 
@@ -281,12 +304,16 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b
         {
             const unsigned pieces = it.n_valid * 8;
             const char *g = reinterpret_cast<const char *>(src_blocks) + (size_t)tid * 16;
-            unsigned d = (unsigned)__cvta_generic_to_shared(coef) + (tid >> 3) * (kStageStride * 2) + (tid & 7) * 16;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(coef) + (tid >> 3) * (kStageStride * 2) + (tid & 7) * 16;
+            if (it.n_valid == T) { // a full chunk: no bounds to test
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if ((unsigned)(tid + k * T) < pieces) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-                g += T * 16;
-                d += (T / 8) * (kStageStride * 2);
+                for (int k = 0; k < 8; ++k)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * (T / 8) * (kStageStride * 2)), "l"(g + k * T * 16) : "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((unsigned)(tid + k * T) < pieces)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * (T / 8) * (kStageStride * 2)), "l"(g + k * T * 16) : "memory");
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
@@ -314,10 +341,10 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b
             const unsigned v_in_seg = it.v_in_seg0 + tid;
             unsigned unit = v_in_seg, slot = 0;
             if (G.bpu > 1) divmod(v_in_seg, G.div_bpu, unit, slot);
-            const int comp = G.comp < 0 ? P.slot_comp[slot] : G.comp;
-            tbl = P.comp_tbl[comp];
-            const int back = G.comp < 0 ? P.slot_back[slot] : 1;
-            const bool first_of_comp = G.comp < 0 ? P.slot_first[slot] != 0 : true;
+            const unsigned sinfo = G.comp < 0 ? slot_tab[slot] : ((unsigned)P.comp_tbl[G.comp] | 0x10100u);
+            tbl = sinfo & 0xFF;
+            const int back = (sinfo >> 8) & 0xFF;
+            const bool first_of_comp = (sinfo >> 16) != 0;
             int prev = 0;
             if (!(unit == 0 && first_of_comp)) prev = tid >= back ? (int)coef[(tid - back) * kStageStride] : (int)__ldg(src_blocks + ((long long)tid - back) * 64);
             dcdiff = (int)(int16_t)(coef[tid * kStageStride] - prev);
@@ -341,7 +368,8 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b
                     int size;
                     uint32_t bits;
                     value_code(dcdiff, size, bits);
-                    first = dc_tab[tbl * 16 + size] | bits;
+                    const uint2 e = dc_tab[tbl * 16 + size];
+                    first = e.x | bits | e.y << 27;
                 }
             }
             maskv[tid] = ((unsigned long long)m_hi << 32) | m_lo;
@@ -423,28 +451,37 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const EntropyBuffers b
                 b.chunk_bits[ci] = total;
                 b.chunk_pool[ci] = (uint32_t)at;
             }
-            for (unsigned wb = 0; wb < total_words; wb += L::kAsmWords) {
+            for (unsigned wb = 0; wb < total_words; wb += L::kAsmWords) { // one pass unless the chunk is larger than the buffer
                 const unsigned nwin = total_words - wb < (unsigned)L::kAsmWords ? total_words - wb : (unsigned)L::kAsmWords;
                 for (unsigned i = tid * 4; i < nwin; i += T * 4) *reinterpret_cast<uint4 *>(asmbuf + i) = make_uint4(0, 0, 0, 0);
                 __syncthreads();
-                if (myb) { // shift this visit's words to bit offset `off` of the chunk; first and last word are shared with the neighbours
+                if (myb) { // shift this visit's words to bit offset `off` of the chunk; only its first and last word are shared with the neighbours
                     const unsigned d0 = off >> 5, dl = (off + myb - 1) >> 5, sft = off & 31;
-                    const unsigned lo = d0 > wb ? d0 : wb, hi = dl < wb + nwin - 1 ? dl : wb + nwin - 1;
-                    if (lo <= hi) {
-                        unsigned jw = lo - d0; // source word that starts in destination word `lo`
-                        auto word = [&](unsigned q) -> uint32_t {
-                            if (q >= nw) return 0u;
-                            if (q < 4) return q == 0 ? pre[0] : (q == 1 ? pre[1] : (q == 2 ? pre[2] : pre[3]));
-                            return __ldcg(mine + q * T);
-                        };
-                        uint32_t prev = jw > 0 ? word(jw - 1) : 0u;
-                        for (unsigned d = lo; d <= hi; ++d, ++jw) {
+                    auto word = [&](unsigned q) -> uint32_t {
+                        if (q >= nw) return 0u;
+                        if (q < 4) return q == 0 ? pre[0] : (q == 1 ? pre[1] : (q == 2 ? pre[2] : pre[3]));
+                        return __ldcg(mine + q * T);
+                    };
+                    if (wb == 0 && dl < nwin) { // the usual case: the whole visit lies in this window
+                        uint32_t prev = pre[0];
+                        atomicOr(asmbuf + d0, prev >> sft);
+                        unsigned jw = 1;
+                        for (unsigned d = d0 + 1; d < dl; ++d, ++jw) {
                             const uint32_t cur = word(jw);
-                            const uint32_t val = sft ? __funnelshift_r(cur, prev, sft) : cur;
-                            const bool owned = 32u * d >= off && 32u * d + 32u <= off + myb;
-                            if (owned) asmbuf[d - wb] = val;
-                            else atomicOr(asmbuf + (d - wb), val);
+                            asmbuf[d] = __funnelshift_r(cur, prev, sft);
                             prev = cur;
+                        }
+                        if (dl > d0) atomicOr(asmbuf + dl, __funnelshift_r(word(jw), prev, sft));
+                    } else {
+                        const unsigned lo = d0 > wb ? d0 : wb, hi = dl < wb + nwin - 1 ? dl : wb + nwin - 1;
+                        if (lo <= hi) {
+                            unsigned jw = lo - d0; // source word that starts in destination word `lo`
+                            uint32_t prev = jw > 0 ? word(jw - 1) : 0u;
+                            for (unsigned d = lo; d <= hi; ++d, ++jw) {
+                                const uint32_t cur = word(jw);
+                                atomicOr(asmbuf + (d - wb), __funnelshift_r(cur, prev, sft));
+                                prev = cur;
+                            }
                         }
                     }
                 }
@@ -470,10 +507,9 @@ __device__ __forceinline__ unsigned lead_len(const EntropyBuffers &b, const DevP
     return b.hdr_len[b.huff_per_image ? img : 0];
 }
 
-__global__ void __launch_bounds__(256) segment_len_kernel(const EntropyBuffers b, unsigned long long n_segs) {
+__global__ void __launch_bounds__(256) segment_len_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_segs) {
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_segs) return;
-    const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.segs_per_image;
     const unsigned s = (unsigned)(g - img * P.segs_per_image);
     const int k = find_scan_by_seg(P, s);
@@ -514,12 +550,11 @@ __device__ __forceinline__ void put_raw(const EntropyBuffers &b, unsigned long l
     atomicOr(b.raw_mask + (pos >> 5), 1u << (pos & 31));
 }
 
-__global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers b, unsigned long long n_segs) {
+__global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_segs) {
     // one warp per segment; lanes stride over the lead bytes (headers can be long: ICC, EXIF)
     const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= n_segs || !stream_fits(b)) return;
-    const DevPlan &P = *b.plan;
     const unsigned long long img = g / P.segs_per_image;
     const unsigned s = (unsigned)(g - img * P.segs_per_image);
     const int k = find_scan_by_seg(P, s);
@@ -551,9 +586,8 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const EntropyBuffers 
 // last stream word of a chunk are shared with its neighbours and are merged with atomicOr (the stream is
 // zero-initialised); words in between are owned and stored. The warp of a segment's first chunk also writes the
 // pad bits of finalize_bit_buffer behind the segment's last bit (writer.rs:138-145: ones up to the byte boundary).
-__global__ void __launch_bounds__(256) place_chunks_kernel(const EntropyBuffers b, unsigned long long n_chunks) {
+__global__ void __launch_bounds__(256) place_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_chunks) {
     if (!stream_fits(b) || (b.status[2] & 4ull)) return;
-    const DevPlan &P = *b.plan;
     const int lane = threadIdx.x & 31;
     const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     uint32_t *stream = reinterpret_cast<uint32_t *>(b.ustream);
@@ -587,18 +621,28 @@ __global__ void __launch_bounds__(256) place_chunks_kernel(const EntropyBuffers 
         const unsigned nw = (bits + 31) >> 5, ndw = (sft + bits + 31) >> 5;
         const bool first_owned = sft == 0, last_owned = ((sft + bits) & 31) == 0;
         uint32_t carry = 0; // source word in front of this step's first one
-        for (unsigned base = 0; base < ndw; base += 32) {
-            const unsigned d = base + lane;
-            const uint32_t cur = d < nw ? __ldg(src + d) : 0u;
-            uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
-            if (lane == 0) prev = carry;
-            carry = __shfl_sync(0xffffffffu, cur, 31);
-            if (d < ndw) {
-                const uint32_t val = sft ? __funnelshift_r(cur, prev, sft) : cur;
-                const uint32_t be = __byte_perm(val, 0, 0x0123);
-                const bool owned = (d > 0 || first_owned) && (d + 1 < ndw || last_owned);
-                if (owned) dst[d] = be;
-                else atomicOr(dst + d, be);
+        // 128 words per step: four independent, coalesced loads per lane are in flight together (the kernel is bound by
+        // load latency, not by bytes)
+        for (unsigned base = 0; base < ndw; base += 128) {
+            uint32_t cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned d = base + 32 * u + lane;
+                cur[u] = d < nw ? __ldg(src + d) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned d = base + 32 * u + lane;
+                uint32_t prev = __shfl_up_sync(0xffffffffu, cur[u], 1);
+                if (lane == 0) prev = carry;
+                carry = __shfl_sync(0xffffffffu, cur[u], 31);
+                if (d < ndw) {
+                    const uint32_t val = sft ? __funnelshift_r(cur[u], prev, sft) : cur[u];
+                    const uint32_t be = __byte_perm(val, 0, 0x0123);
+                    const bool owned = (d > 0 || first_owned) && (d + 1 < ndw || last_owned);
+                    if (owned) dst[d] = be;
+                    else atomicOr(dst + d, be);
+                }
             }
         }
     }
@@ -733,14 +777,13 @@ __device__ __forceinline__ unsigned ff_before_in_chunk(const EntropyBuffers &b, 
 
 // byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
 // bytes that precede it
-__global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers b, unsigned n_images) {
+__global__ void __launch_bounds__(128) file_offsets_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned n_images) {
     if (!stream_fits(b)) return;
     const unsigned long long bytes = stream_bytes(b);
     // one warp per file boundary; lanes stride over the (< kStuffChunk) bytes between the chunk start and it
     const unsigned img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (img > n_images) return;
-    const DevPlan &P = *b.plan;
     const unsigned long long pos = img == n_images ? bytes : b.segpos[(unsigned long long)img * P.segs_per_image];
     const unsigned long long chunk = pos / kStuffChunk;
     const unsigned ff = ff_before_in_chunk(b, pos, lane);
@@ -748,12 +791,11 @@ __global__ void __launch_bounds__(128) file_offsets_kernel(const EntropyBuffers 
 }
 
 // final byte offset of the first segment of every scan of image 0 (+ the end): the pieces of a strip
-__global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers b, unsigned long long *offs) {
+__global__ void __launch_bounds__(128) scan_offsets_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long *offs) {
     if (!stream_fits(b)) return;
     const unsigned long long bytes = stream_bytes(b);
     const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const DevPlan &P = *b.plan;
     if (k > (unsigned)P.n_scans) return;
     const unsigned long long pos = k == (unsigned)P.n_scans ? bytes : b.segpos[P.scans[k].seg_base];
     const unsigned long long chunk = pos / kStuffChunk;
@@ -767,10 +809,9 @@ __global__ void __launch_bounds__(128) scan_offsets_kernel(const EntropyBuffers 
 // with no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL for
 // runs > 15, EOB when a band ends in zeros. Bins: [image][table][dc|ac][257]. One launch for the whole batch:
 // blockIdx.y walks the images, a CTA never straddles two of them.
-__global__ void __launch_bounds__(256) histogram_kernel(const DevPlan *plan, const int16_t *coef, unsigned n_images, uint32_t *hist,
+__global__ void __launch_bounds__(256) histogram_kernel(const __grid_constant__ DevPlan P, const int16_t *coef, unsigned n_images, uint32_t *hist,
                                                         int bands, int per_band) {
     __shared__ unsigned sh[2 * 2 * 257];
-    const DevPlan &P = *plan;
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; // block inside the image
     for (unsigned img = blockIdx.y; img < n_images; img += gridDim.y) {
         for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x) sh[i] = 0;
@@ -823,13 +864,13 @@ __global__ void __launch_bounds__(256) histogram_kernel(const DevPlan *plan, con
 
 static inline unsigned grid_for(unsigned long long n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
-cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hp, const int16_t *coef, uint32_t n_images, uint32_t *hist,
+cudaError_t launch_histogram(const DevPlan &hp, const int16_t *coef, uint32_t n_images, uint32_t *hist,
                              cudaStream_t stream) {
     // sequential / progressive plans only (optimized tables never code interleaved)
     const int bands = hp.spg > 1 ? hp.spg - 1 : 1;
     const int per_band = bands > 1 ? 64 / bands : 64;
     dim3 grid(grid_for(hp.blocks_per_image, 256), n_images < 32768 ? n_images : 32768);
-    histogram_kernel<<<grid, 256, 0, stream>>>(plan, coef, n_images, hist, bands, per_band);
+    histogram_kernel<<<grid, 256, 0, stream>>>(hp, coef, n_images, hist, bands, per_band);
     return cudaGetLastError();
 }
 
@@ -898,14 +939,14 @@ cudaError_t coder_launch_config(const DevPlan &hp, uint32_t n, CoderLaunch &cfg)
 }
 cudaError_t launch_encode_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, const CoderLaunch &cfg, cudaStream_t s) {
     const unsigned long long n_items = (unsigned long long)hp.items_per_image * n;
-#define JPGB_RUN(T, F) encode_chunks_kernel<T, F><<<cfg.grid, T, cfg.smem, s>>>(b, n_items)
+#define JPGB_RUN(T, F) encode_chunks_kernel<T, F><<<cfg.grid, T, cfg.smem, s>>>(b, hp, n_items)
     JPGB_CODER_DISPATCH(JPGB_RUN);
 #undef JPGB_RUN
     return cudaGetLastError();
 }
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long ns = (unsigned long long)hp.segs_per_image * n;
-    segment_len_kernel<<<grid_for(ns, 256), 256, 0, s>>>(b, ns);
+    segment_len_kernel<<<grid_for(ns, 256), 256, 0, s>>>(b, hp, ns);
     return cudaGetLastError();
 }
 cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t s) {
@@ -916,13 +957,13 @@ cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, 
 }
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long ns = (unsigned long long)hp.segs_per_image * n;
-    segment_lead_kernel<<<grid_for(ns * 32, 128), 128, 0, s>>>(b, ns);
+    segment_lead_kernel<<<grid_for(ns * 32, 128), 128, 0, s>>>(b, hp, ns);
     return cudaGetLastError();
 }
 cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long nc = (unsigned long long)hp.chunks_per_image * n;
     const unsigned long long ctas = (nc + 7) / 8; // one warp per chunk, grid-stride beyond 64 K CTAs
-    place_chunks_kernel<<<(unsigned)(ctas < 65536 ? (ctas ? ctas : 1) : 65536), 256, 0, s>>>(b, nc);
+    place_chunks_kernel<<<(unsigned)(ctas < 65536 ? (ctas ? ctas : 1) : 65536), 256, 0, s>>>(b, hp, nc);
     return cudaGetLastError();
 }
 cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t s) {
@@ -935,11 +976,11 @@ cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hp, unsigned long long *offs, cudaStream_t s) {
-    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, offs);
+    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, hp, offs);
     return cudaGetLastError();
 }
-cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &, uint32_t n, cudaStream_t s) {
-    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, n);
+cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
+    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, hp, n);
     return cudaGetLastError();
 }
 

@@ -15,9 +15,9 @@ cudaError_t launch_stage_a(const StageAParams &p, uint32_t n_images, cudaStream_
 // Huffman code tables as the kernels see them: [image][table 0|1][class dc|ac][256] of (size<<16)|code
 constexpr size_t kHuffWordsPerImage = 2 * 2 * 256;
 
-// Buffers of one encode call (all device pointers). Sizes are in the comments; `n` = images.
+// Buffers of one encode call (all device pointers). Sizes are in the comments; `n` = images. The plan itself
+// (DevPlan, ~14 KB) travels to the kernels as a __grid_constant__ parameter: every field is a constant-bank operand.
 struct EntropyBuffers {
-    const DevPlan *plan;           // device copy of the plan
     const int16_t *coef;           // n * blocks_per_image * 64
     const uint32_t *huff;          // n_huff * kHuffWordsPerImage; n_huff is 1 (shared) or n (optimized)
     int huff_per_image;            // 0: all images share tables[0]; 1: one set per image
@@ -55,7 +55,7 @@ constexpr int kSlotWords = 56;
 constexpr int kStuffChunk = 4096; // bytes of unstuffed stream per CTA in the stuffing kernels
 
 // entropy.cu
-cudaError_t launch_histogram(const DevPlan *plan, const DevPlan &hplan, const int16_t *coef, uint32_t n_images,
+cudaError_t launch_histogram(const DevPlan &hplan, const int16_t *coef, uint32_t n_images,
                              uint32_t *hist /* n * 2 tables * 2 classes * 257 */, cudaStream_t stream);
 // persistent coding kernel: grid = what coder_grid() returns for this plan; `b.scratch` holds coder_scratch_bytes()
 struct CoderLaunch {
