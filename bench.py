@@ -38,6 +38,8 @@ WORKLOADS = {
            "1 x 4096x4096 RGB q85 4:2:0 optimized Huffman, restart 64 (BASELINE config 2)"),
     "c3": (1920, 1080, "rgb", dict(quality=90, sampling=(2, 2)), 1024,
            "batch of 1920x1080 RGB q90 4:2:0 baseline frames, sharded by image (BASELINE config 3)"),
+    "c3o": (1920, 1080, "rgb", dict(quality=90, sampling=(2, 2), optimize_huffman=True), 1024,
+            "batch of 1920x1080 RGB q90 4:2:0 frames with per-image optimized Huffman tables (histogram + Annex K.2 on the device)"),
     "c4a": (8192, 8192, "luma", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
             "1 x 8192x8192 grayscale q95 custom tables (BASELINE config 4a)"),
     "c4b": (8192, 8192, "cmyk_as_ycck", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
@@ -211,7 +213,9 @@ def run_product(args):
     order = order_global[lo:hi]
     order_weak = [(i + rank) % n_distinct for i in range(weak_batch)]
 
-    stream = torch.cuda.current_stream()
+    # a stream of our own (the legacy default stream cannot be captured into the CUDA graph the library replays)
+    stream = torch.cuda.Stream(device=dev_t)
+    torch.cuda.set_stream(stream)
     device = je.Device(local, cuda_stream=stream.cuda_stream)
     enc = make_encoder(cfg, device)
     ct = CT[color][1]
@@ -247,9 +251,11 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_device(n_frames):
+    def timed_device(n_frames, stage_timers=False):
         """K timed steps of the device-resident path over the first n_frames resident frames: (ms per step max over
-        ranks, per-stage ms, launches)."""
+        ranks, per-stage ms, launches). With stage_timers the library brackets every stage with CUDA events (and
+        launches kernel by kernel instead of replaying its CUDA graph): used for the breakdown, not for `value`."""
+        device.set_timing(stage_timers)
         for _ in range(args.warmup):
             enc.encode_batch_device(d_in.data_ptr(), stride, n_frames, width, height, ct)
         barrier()
@@ -271,14 +277,15 @@ def run_product(args):
         return ms_ / args.steps, stage_ms_, launches_
 
     # ---- device-resident timing ----
-    device.set_timing(True)
     # the clock sampler (an nvidia-smi process) is started before the warm-up: its start-up initialises NVML on every
     # GPU of the box and takes driver locks for tens of ms, which must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms_per_step, stage_ms, launches = timed_device(batch)
+    ms_per_step, _, launches = timed_device(batch)
+    _, stage_ms, _ = timed_device(batch, stage_timers=True)  # second pass: per-stage breakdown and the roofline numerator
+    device.set_timing(False)
     if rank == 0:
         # the timed region is tens of milliseconds: keep the same work running (un-timed) for about a
         # second so that the 50 ms clock samples are taken under this load
@@ -473,7 +480,8 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         width = height = args.size
     ct = CT[color][1]
     bpp = BPP[color]
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev_t)
+    torch.cuda.set_stream(stream)
     device = je.Device(local, cuda_stream=stream.cuda_stream)
     enc = make_encoder(cfg, device)
     strips = enc.plan_strips(width, height, ct, world)
@@ -537,7 +545,7 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
             dist.barrier()
         torch.cuda.synchronize()
 
-    device.set_timing(True)
+    device.set_timing(False)
     sampler = ClockSampler(local)  # started before the warm-up, see run_batch
     if rank == 0 and not extra:
         sampler.start()
@@ -546,14 +554,21 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms, launches = {}, 0
+    launches = 0
     e0.record(stream)
     for _ in range(args.steps):
-        _, l, tm = step(timed=True)
+        _, l, _ = step(timed=True)
         launches += l
+    e1.record(stream)
+    barrier()
+    # second pass with the library's per-stage events (kernel-by-kernel launches instead of the graph replay): breakdown only
+    device.set_timing(True)
+    stage_ms = {}
+    for _ in range(args.steps):
+        _, _, tm = step()
         for k, v in (tm or {}).items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
-    e1.record(stream)
+    device.set_timing(False)
     barrier()
     ms = e0.elapsed_time(e1)
     if world > 1:

@@ -43,7 +43,8 @@ struct EntropyBuffers {
     // capacities (bytes) of ustream / out and the status block the kernels report into: the host sizes the
     // buffers from the previous call and checks `status` once at the end instead of syncing mid-pipeline
     unsigned long long ustream_cap, out_cap, n_segs_total;
-    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] overflow flags (1: ustream, 2: out, 4: pool, 8: a segment over 4 GiB),
+    // [0] unstuffed bytes, [1] data 0xFF bytes, [2] flags (1: ustream, 2: out, 4: pool overflow; 8: a segment over 4 GiB;
+    // 16: an optimized Huffman code does not fit),
     // [3] scan error, [4] work-item ticket of the coding kernel, [5] pool cursor (16-byte units)
     unsigned long long *status;
     size_t scan_tmp_bytes;
@@ -73,6 +74,12 @@ cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t stream);
 cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, unsigned long long *offs,
                                 cudaStream_t stream);
 cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+
+// tables.cu -- optimized Huffman tables (Annex K.2), kernel-format code words and the file header with its DHT
+// segments, one CTA per image. hist: [image][table][dc|ac][257] (hist_per_image = 0: one histogram for all).
+cudaError_t launch_build_tables(const uint32_t *hist, int hist_per_image, int n_tables, uint32_t n_images, uint32_t *huff, const uint8_t *head,
+                                uint32_t head_len, const uint8_t *tail, uint32_t tail_len, uint8_t *hdr, uint32_t hdr_stride, uint32_t *hdr_len,
+                                unsigned long long *status, cudaStream_t stream);
 
 // scan.cu -- device-wide exclusive prefix sum of u32 into u64; out has n + 1 entries (out[n] = total)
 size_t scan_tmp_bytes(uint64_t n);
