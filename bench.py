@@ -507,6 +507,8 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         return encode_strip(d_strip.data_ptr())
 
     gather_events = []
+    # the assembled file is at most the raw strip sizes; rank 0 owns the target, the other ranks map it over NVLink (CUDA IPC)
+    pg = sharding.PeerGather(device, max(width * height * bpp // 2, 1 << 20), rank, world, dev_t) if world > 1 else None
 
     def step(gather=True, timed=False):
         d_bytes, offs = encode_once()
@@ -514,23 +516,31 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         tm = device.last_timing()
         out = None
         if world > 1 and gather:
-            # wrap the context-owned device buffer (no copy) and gather the pieces to rank 0 over NVLink
-            local_bytes = _as_tensor(d_bytes, offs[-1], dev_t)
+            # device-placed gather: one NCCL all-gather of the piece offsets, then every rank's kernel stores its pieces at
+            # their scan-major place inside rank 0's buffer through a peer pointer; one barrier
             if timed:
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record(stream)
-            out = sharding.gather_strip_pieces(local_bytes, offs, rank, world, dev_t)
+            pg.gather()
+            pg.barrier()
+            launches += 1
             if timed:
                 g1.record(stream)
                 gather_events.append((g0, g1))
+            out = pg
         elif gather:
             out = _as_tensor(d_bytes, offs[-1], dev_t)
         return out, launches, tm
 
+    def fetch(out):
+        """rank 0: the assembled file as a device tensor"""
+        return out.result() if world > 1 else out
+
     # parity gate (un-timed): the assembled file must equal the oracle's for the whole image
     out, _, _ = step()
+    torch.cuda.synchronize()
     if rank == 0:
-        got = bytes(out.cpu().numpy().tobytes())
+        got = bytes(fetch(out).cpu().numpy().tobytes())
         if not args.skip_parity:
             full = torch.cat([images.synth_frame_torch(width, height, bpp, seed=seed, row0=a, rows=b, device=dev_t).cpu()
                               for a, b in strips]).numpy()
@@ -602,7 +612,9 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         d_stage.copy_(h_strip, non_blocking=True)
         d_bytes, offs = encode_strip(d_stage.data_ptr())
         if world > 1:
-            o = sharding.gather_strip_pieces(_as_tensor(d_bytes, offs[-1], dev_t), offs, rank, world, dev_t)
+            pg.gather()
+            pg.barrier()
+            o = pg.result() if rank == 0 else None
         else:
             o = _as_tensor(d_bytes, offs[-1], dev_t)
         if rank == 0:
@@ -613,6 +625,13 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
         t = torch.tensor([e2e_s], device=dev_t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    if pg:  # the peers unmap rank 0's buffer before rank 0 frees it
+        torch.cuda.synchronize()
+        if rank != 0:
+            pg.close()
+        dist.barrier()
+        if rank == 0:
+            pg.close()
     if rank != 0:
         if world > 1 and not extra:
             dist.destroy_process_group()
@@ -633,11 +652,12 @@ def run_strips(args, rank, world, local, dev_t, extra=False):
                    "strips": [[int(a), int(b)] for a, b in strips], "settings": cfg, "bytes_out": out_bytes,
                    "l2": "strip input %.0f MB per GPU, larger than L2" % (width * rows * bpp / 1e6),
                    "collective": ("all-reduce of the 4 x 257 symbol histogram + all_gather of edge DCs, then " if optimized else "")
-                   + "one all_gather of piece sizes + one NCCL send per non-zero rank (gather to rank 0)"},
+                   + ("one NCCL all-gather of the piece offsets (device tensors), then every rank's kernel stores its pieces at their "
+                      "scan-major place in rank 0's buffer through a CUDA-IPC peer pointer over NVLink, one barrier" if world > 1 else "none at N = 1")},
         "clocks": clocks,
         "e2e": {"value": mp * e2e_steps / e2e_s, "unit": "megapixels/s", "h2d_bytes_per_step": width * height * bpp,
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "api": "pinned host strip -> jpgb_encode_strip_device -> NCCL gather -> host file on rank 0"},
+                "api": "pinned host strip -> jpgb_encode_strip_device -> device-placed gather -> host file on rank 0"},
         "gpu_launches": launches,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "gather_ms_per_step": gather_ms,

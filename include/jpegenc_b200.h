@@ -179,6 +179,26 @@ int jpgb_merge_strip_histograms(const jpgb_params *p, uint32_t n_strips, const u
 int jpgb_encode_strip_device_optimized(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
                                        const uint32_t hist_total[JPGB_HIST_WORDS], const void **d_bytes, uint64_t *piece_offsets);
 
+/* ---- gathering the strips' pieces on the root GPU, device to device (the "peer copy" of BASELINE config 5) ----
+ * The assembled file is scan-major: for every scan, the pieces of strips 0..n-1 in order. Each GPU stores its own
+ * pieces straight into the root's buffer:
+ *   root:   jpgb_gather_target_create -> a device buffer + a 64-byte CUDA IPC handle that the other processes receive
+ *           (jpeg_encoder_b200/sharding.py broadcasts it once over torch.distributed);
+ *   others: jpgb_gather_target_open   -> the same memory as a peer pointer (NVLink);
+ *   every step, every rank: piece offsets of the strip just encoded stay on the device (jpgb_last_piece_offsets_device),
+ *           are all-gathered by the caller into one table of world * (n_scans + 1) u64 (one NCCL all-gather: the only
+ *           collective of the path), then jpgb_gather_place_pieces launches one kernel that stores this rank's pieces
+ *           at their final offsets. A barrier of the caller's choice tells the root when every rank is done.
+ * All of it is asynchronous on the context's stream; nothing here synchronises with the host. */
+int jpgb_gather_target_create(jpgb_encoder *enc, size_t capacity, void **d_target, uint8_t ipc_handle[64]);
+int jpgb_gather_target_open(jpgb_encoder *enc, const uint8_t ipc_handle[64], void **d_target);
+int jpgb_gather_target_close(jpgb_encoder *enc, void *d_target, int opened_from_handle);
+int jpgb_last_piece_offsets_device(jpgb_encoder *enc, const uint64_t **d_offsets, uint32_t *n_scans);
+/* d_table: world * (n_scans + 1) piece offsets in rank order (device memory). d_total (optional, device): receives the
+ * size of the assembled file. Pieces are read from the output of the last jpgb_encode_strip_device* call. */
+int jpgb_gather_place_pieces(jpgb_encoder *enc, void *d_target, size_t target_capacity, const uint64_t *d_table, uint32_t world,
+                             uint32_t rank, uint64_t *d_total);
+
 /* Copy `n` bytes of context-owned (or any) device memory to host memory; synchronous on the context's stream. */
 int jpgb_download(jpgb_encoder *enc, const void *d_src, size_t n, void *host_dst);
 

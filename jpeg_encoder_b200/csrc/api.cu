@@ -107,6 +107,7 @@ struct jpgb_encoder {
     float last_ms[JPGB_N_STAGES] = {};
     bool have_timing = false;
     uint32_t launches = 0;
+    uint32_t last_piece_scans = 0; // scans of the last strip encode (its piece offsets are in piece_off)
     // replay of the launch sequence behind stage A as a CUDA graph (same settings, batch size and buffers)
     bool graphs_ok = true;
     struct CachedGraph {
@@ -535,7 +536,10 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     enc->pool_ratio = std::max(enc->pool_ratio * 0.98, 1.1 * (double)((pool_used > n_chunks ? pool_used - n_chunks : 0) * 16) / (double)std::max<uint64_t>(raw_bytes, 1));
     enc->ucap_ratio = std::max(enc->ucap_ratio * 0.98, 1.15 * (double)ubytes / (double)std::max<uint64_t>(raw_bytes, 1));
     CK(cudaStreamSynchronize(st), "final sync");
-    if (piece_offsets) piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
+    if (piece_offsets) {
+        piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
+        enc->last_piece_scans = (uint32_t)plan.scans.size();
+    }
     offsets.assign(enc->h_small.as<uint64_t>() + 16, enc->h_small.as<uint64_t>() + 16 + n + 1);
     enc->out_total = total;
     if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
@@ -1012,6 +1016,67 @@ int jpgb_merge_strip_histograms(const jpgb_params *p, uint32_t n_strips, const u
             dc[category(first)] -= 1;             // the strip counted its first block against a predictor of 0
             dc[category(first - prev_last)] += 1; // the whole image chains it to the block before
         }
+    return JPGB_OK;
+}
+
+int jpgb_gather_target_create(jpgb_encoder *enc, size_t capacity, void **d_target, uint8_t ipc_handle[64]) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_target || !ipc_handle || capacity == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI carries the IPC handle as 64 bytes");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    void *p = nullptr;
+    CK(cudaMalloc(&p, capacity + 64), "alloc gather target");
+    cudaIpcMemHandle_t h;
+    const cudaError_t ce = cudaIpcGetMemHandle(&h, p);
+    if (ce != cudaSuccess) {
+        cudaFree(p);
+        return fail_cuda(enc, ce, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(ipc_handle, &h, 64);
+    *d_target = p;
+    return JPGB_OK;
+}
+
+int jpgb_gather_target_open(jpgb_encoder *enc, const uint8_t ipc_handle[64], void **d_target) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_target || !ipc_handle) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer access over NVLink)");
+    *d_target = p;
+    return JPGB_OK;
+}
+
+int jpgb_gather_target_close(jpgb_encoder *enc, void *d_target, int opened_from_handle) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_target) return JPGB_OK;
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(enc->stream), "sync before releasing the gather target");
+    if (opened_from_handle) CK(cudaIpcCloseMemHandle(d_target), "cudaIpcCloseMemHandle");
+    else CK(cudaFree(d_target), "free gather target");
+    return JPGB_OK;
+}
+
+int jpgb_last_piece_offsets_device(jpgb_encoder *enc, const uint64_t **d_offsets, uint32_t *n_scans) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_offsets || !n_scans || !enc->piece_off.p || enc->last_piece_scans == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "no strip has been encoded on this context");
+    *d_offsets = enc->piece_off.as<uint64_t>();
+    *n_scans = enc->last_piece_scans;
+    return JPGB_OK;
+}
+
+int jpgb_gather_place_pieces(jpgb_encoder *enc, void *d_target, size_t target_capacity, const uint64_t *d_table, uint32_t world, uint32_t rank,
+                             uint64_t *d_total) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!d_target || !d_table || world == 0 || rank >= world || enc->last_piece_scans == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "bad gather arguments");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    CK(enc->aux_status.reserve(kStatusWords * 8), "alloc status");
+    CK(launch_place_pieces(enc->out.as<uint8_t>(), static_cast<uint8_t *>(d_target), target_capacity, reinterpret_cast<const unsigned long long *>(d_table),
+                           world, rank, enc->last_piece_scans, reinterpret_cast<unsigned long long *>(d_total),
+                           enc->aux_status.as<unsigned long long>() + 4, enc->stream),
+       "piece placement launch");
     return JPGB_OK;
 }
 

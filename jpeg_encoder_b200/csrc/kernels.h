@@ -81,6 +81,10 @@ cudaError_t launch_build_tables(const uint32_t *hist, int hist_per_image, int n_
                                 uint32_t head_len, const uint8_t *tail, uint32_t tail_len, uint8_t *hdr, uint32_t hdr_stride, uint32_t *hdr_len,
                                 unsigned long long *status, cudaStream_t stream);
 
+// gather.cu -- a rank's pieces stored at their place in the assembled file (possibly in a peer GPU's memory)
+cudaError_t launch_place_pieces(const uint8_t *src, uint8_t *dst, unsigned long long dst_cap, const unsigned long long *table, unsigned world,
+                                unsigned rank, unsigned n_scans, unsigned long long *total_out, unsigned long long *status, cudaStream_t stream);
+
 // scan.cu -- device-wide exclusive prefix sum of u32 into u64; out has n + 1 entries (out[n] = total)
 size_t scan_tmp_bytes(uint64_t n);
 cudaError_t launch_exclusive_scan(const uint32_t *in, unsigned long long *out, uint64_t n, void *tmp, cudaStream_t stream,

@@ -200,6 +200,11 @@ def load_library():
     l.jpgb_strip_histogram_device.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Strip), vp, C.POINTER(C.c_uint32), C.POINTER(C.c_int16)]
     l.jpgb_merge_strip_histograms.argtypes = [C.POINTER(_Params), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int16), C.POINTER(C.c_uint32)]
     l.jpgb_download.argtypes = [vp, vp, C.c_size_t, vp]
+    l.jpgb_gather_target_create.argtypes = [vp, C.c_size_t, C.POINTER(vp), u8p]
+    l.jpgb_gather_target_open.argtypes = [vp, u8p, C.POINTER(vp)]
+    l.jpgb_gather_target_close.argtypes = [vp, vp, C.c_int]
+    l.jpgb_last_piece_offsets_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
+    l.jpgb_gather_place_pieces.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_uint32, vp]
     l.jpgb_coef_layout_for.argtypes = [C.POINTER(_Params), C.POINTER(_CoefLayout)]
     l.jpgb_stage_a_device.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, C.c_uint32, vp]
     l.jpgb_encoder_set_timing.argtypes = [vp, C.c_int]

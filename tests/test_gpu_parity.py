@@ -412,6 +412,47 @@ def test_strips_concatenate_to_the_whole_image(name, color, w, h, cfg, max_strip
     assert got == oracle_encode(img, w, h, color, cfg)
 
 
+def test_device_placed_gather_of_strip_pieces():
+    """csrc/gather.cu on one GPU: the strips are encoded one after the other, and each time the placement kernel stores
+    that strip's pieces at their final scan-major offsets inside the gather target, exactly as rank i of an N-GPU job
+    does through a peer pointer. The assembled buffer must be the whole-image file."""
+    import ctypes as C
+    import torch
+    import jpeg_encoder_b200 as je
+    from jpeg_encoder_b200 import sharding
+    w, h, color = 640, 496, "rgb"
+    cfg = dict(quality=85, sampling=(2, 2), progressive_scans=4, restart_interval=40)
+    img = _img(color, w, h, seed=33)
+    want = oracle_encode(img, w, h, color, cfg)
+    enc = make_encoder(cfg)
+    ct = CT[color][1]
+    dev = je.default_device(0)
+    strips = enc.plan_strips(w, h, ct, 5)
+    assert len(strips) > 2
+    flat = np.ascontiguousarray(img).reshape(h, -1)
+    d_px = [torch.from_numpy(flat[r0:r0 + rows].copy()).cuda() for r0, rows in strips]
+    torch.cuda.synchronize()
+    table = []
+    for i, (r0, rows) in enumerate(strips):  # pass 1: every strip's piece offsets (what the all-gather distributes)
+        _, offs = enc.encode_strip_device(d_px[i].data_ptr(), i, len(strips), r0, rows, w, h, ct)
+        table.append(list(offs))
+    dest, total = sharding.piece_destinations(table)
+    assert total == len(want)
+    target, handle = C.c_void_p(), (C.c_uint8 * 64)()
+    assert dev.lib.jpgb_gather_target_create(dev.handle, total + 1000, C.byref(target), handle) == 0
+    d_table = torch.tensor([v for row in table for v in row], dtype=torch.int64, device="cuda")
+    d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for i, (r0, rows) in enumerate(strips):  # pass 2: encode again, place as "rank i"
+        enc.encode_strip_device(d_px[i].data_ptr(), i, len(strips), r0, rows, w, h, ct)
+        rc = dev.lib.jpgb_gather_place_pieces(dev.handle, target, total + 1000, C.c_void_p(d_table.data_ptr()), len(strips), i, C.c_void_p(d_total.data_ptr()))
+        assert rc == 0, dev.last_error()
+    got = dev.download(target.value, total)
+    assert int(d_total.item()) == total
+    assert got == want
+    assert dev.lib.jpgb_gather_target_close(dev.handle, target, 0) == 0
+
+
 def test_cpp_mirror_on_gpu(tmp_path):
     import os
     import subprocess

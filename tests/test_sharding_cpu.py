@@ -124,3 +124,25 @@ def test_gather_strip_pieces_gloo_world2():
         assert p.exitcode == 0
     exp = sharding.assemble_pieces([[bytes([10 * r + k]) * (3 + 2 * r + k) for k in range(3)] for r in range(world)])
     assert got == exp
+
+
+def test_piece_destinations_is_the_scan_major_order():
+    """The placement arithmetic of the device gather (csrc/gather.cu, restated in sharding.piece_destinations) against
+    plain concatenation: piece k of rank r starts where assemble_pieces puts it."""
+    import random
+    from jpeg_encoder_b200 import sharding
+    rnd = random.Random(7)
+    for world, n_scans in ((1, 1), (2, 3), (8, 12), (5, 7)):
+        pieces = [[bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 40))) for _ in range(n_scans)] for _ in range(world)]
+        table = []
+        for r in range(world):
+            offs = [0]
+            for k in range(n_scans):
+                offs.append(offs[-1] + len(pieces[r][k]))
+            table.append(offs)
+        dest, total = sharding.piece_destinations(table)
+        want = sharding.assemble_pieces(pieces)
+        assert total == len(want)
+        for r in range(world):
+            for k in range(n_scans):
+                assert want[dest[r][k]:dest[r][k] + len(pieces[r][k])] == pieces[r][k]
