@@ -606,10 +606,8 @@ void Plan::fill_stage_a(StageAParams &a) const {
             }
     }
     a.tasks_per_group = n;
-    // Fast kernel: Luma, the RGB family and CmykAsYcck with luma factors in {1,2}. Same number of warp
-    // tasks per 32-MCU group; a task is then (component, v, run of 32 consecutive blocks).
-    const bool fast_ct = p.color_type == JPGB_LUMA || (p.color_type >= JPGB_RGB && p.color_type <= JPGB_BGRA) ||
-                         p.color_type == JPGB_CMYK_AS_YCCK;
+    // Warp kernel: every packed ColorType with luma factors in {1,2}; a task is (component, v, run of 32 consecutive blocks).
+    const bool fast_ct = true; // every ColorType has a warp-kernel instantiation; planar input and factors of 4 do not
     const char *fg = std::getenv("JPGB_FORCE_GENERIC_STAGE_A"); // test hook
     a.use_fast = !planar && fast_ct && hmax <= 2 && vmax <= 2 && !force_generic_stage_a && !(fg && fg[0] == '1');
     // CTA tile: `groups` x 32 MCUs wide, one MCU row high; aim for ~24 KB of pixels in shared memory

@@ -268,8 +268,16 @@ struct ChromaConsts;
 
 template <int CT>
 struct Fmt {
-    static constexpr int BPP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR) ? 3 : 4);
+    static constexpr int BPP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR || CT == JPGB_YCBCR) ? 3 : 4);
     static constexpr bool BGR = CT == JPGB_BGR || CT == JPGB_BGRA;
+    // formats whose samples are pixel bytes taken verbatim (Ycbcr, Ycck) or inverted (Cmyk): image_buffer.rs:206-257, 288-313
+    static constexpr bool BYTES = CT == JPGB_YCBCR || CT == JPGB_YCCK || CT == JPGB_CMYK;
+    static constexpr int NCOMP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_CMYK_AS_YCCK || CT == JPGB_YCCK || CT == JPGB_CMYK) ? 4 : 3);
+    // components that carry the sampling factor (luma, and K; for Cmyk only K -- encoder.rs:569-619) and the 1x1 ones
+    static constexpr int NFULL = (CT == JPGB_CMYK_AS_YCCK || CT == JPGB_YCCK) ? 2 : 1;
+    static constexpr int NSUB = NCOMP == 1 ? 0 : (CT == JPGB_CMYK ? 3 : 2);
+    __host__ __device__ static constexpr int full_comp(int i) { return CT == JPGB_CMYK ? 3 : (i == 0 ? 0 : 3); }
+    __host__ __device__ static constexpr int sub_comp(int i) { return CT == JPGB_CMYK ? i : 1 + i; }
 };
 
 // sample I of a block row from the row's pixel words (compile-time I: every byte offset is static)
@@ -397,6 +405,64 @@ __device__ __forceinline__ void load_row(const uint8_t *row, int *s, const Chrom
     else sample_row<CT, ROLE, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
 }
 
+// ---- verbatim / inverted byte formats: sample = byte `coff` of the pixel, xor `xorv` (0xFF inverts: 255 - x) ----
+// coff may differ between the lanes of a warp (two components share a task when chroma is horizontally decimated):
+// the byte is picked with PRMT on a register selector out of the pixel's word and the word behind it.
+template <int BPP, int SX, int I, int NW>
+__device__ __forceinline__ int byte_at(const uint32_t (&w)[NW], unsigned coff, unsigned xorv) {
+    constexpr int O = I * SX * BPP;
+    constexpr int W0 = O >> 2, W1 = (W0 + 1 < NW) ? W0 + 1 : W0;
+    return (int)((__byte_perm(w[W0], w[W1], (O & 3) + coff) ^ xorv) & 0xFFu);
+}
+template <int BPP, int SX, int NW, int... Is>
+__device__ __forceinline__ void byte_row(const uint32_t (&w)[NW], int *s, unsigned coff, unsigned xorv, std::integer_sequence<int, Is...>) {
+    ((s[Is] = byte_at<BPP, SX, Is, NW>(w, coff, xorv)), ...);
+}
+template <int BPP, int SX>
+__device__ __forceinline__ void load_row_bytes(const uint8_t *row, int *s, unsigned coff, unsigned xorv) {
+    constexpr int NW = (((7 * SX + 1) * BPP) + 3) / 4;
+    uint32_t w[NW];
+    if constexpr (BPP == 3 && SX == 1) {
+        const uint2 *r = reinterpret_cast<const uint2 *>(row);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint2 a = r[i];
+            w[2 * i] = a.x;
+            w[2 * i + 1] = a.y;
+        }
+    } else if constexpr (BPP == 3) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint4 a = r[i];
+            w[4 * i] = a.x;
+            w[4 * i + 1] = a.y;
+            w[4 * i + 2] = a.z;
+            if (4 * i + 3 < NW) w[4 * i + 3] = a.w;
+        }
+    } else if constexpr (SX == 1) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 a = r[i];
+            w[4 * i] = a.x;
+            w[4 * i + 1] = a.y;
+            w[4 * i + 2] = a.z;
+            w[4 * i + 3] = a.w;
+        }
+    } else { // 4 bytes per pixel, every other pixel
+        const uint32_t *r = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = (i & 1) ? 0u : r[i];
+    }
+    byte_row<BPP, SX, NW>(w, s, coff, xorv, std::make_integer_sequence<int, 8>{});
+}
+template <int BPP, int SX, int SY>
+__device__ __forceinline__ void load_block_bytes(const uint8_t *base, int pitch, int (&v)[64], unsigned coff, unsigned xorv) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) load_row_bytes<BPP, SX>(base + y * SY * pitch, &v[y * 8], coff, xorv);
+}
+
 template <int CT, int ROLE, int SX, int SY>
 __device__ __forceinline__ void load_block(const uint8_t *base, int pitch, int (&v)[64], const ChromaConsts *cc = nullptr) {
 #pragma unroll
@@ -490,7 +556,8 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = Fmt<CT>::BPP;
     constexpr bool SUB = HS * VS > 1;
-    constexpr int NCOMP = CT == JPGB_LUMA ? 1 : (CT == JPGB_CMYK_AS_YCCK ? 4 : 3);
+    constexpr int NCOMP = Fmt<CT>::NCOMP;
+    constexpr bool BYTES = Fmt<CT>::BYTES;
     constexpr int MR = warp_tile_mcu_rows<CT, HS, VS>(); // MCU rows per warp tile (small tiles take several)
     constexpr int MROWS = 8 * VS;               // pixel rows of one MCU row
     constexpr int ROWS = MROWS * MR;
@@ -498,14 +565,15 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     constexpr int TILE_BYTES = PITCH * ROWS;
     constexpr int MCUS = 32 / HS;               // MCUs per warp tile
     // tasks of one warp tile: luma rows, [K rows], then chroma
-    constexpr int N_FULL = (NCOMP == 4 ? 2 : 1) * VS;
-    constexpr int N_CHROMA = NCOMP == 1 ? 0 : (SUB && HS == 2 ? 1 : 2); // Cb+Cr share a task when 16 blocks each
+    constexpr int N_FULL = Fmt<CT>::NFULL * VS;
+    constexpr bool PAIRED = SUB && HS == 2; // two 1x1 components share a task (16 blocks each) when chroma is horizontally decimated
+    constexpr int N_CHROMA = PAIRED ? (Fmt<CT>::NSUB + 1) / 2 : Fmt<CT>::NSUB;
     constexpr int N_TASKS_ROW = N_FULL + N_CHROMA;
     constexpr int N_TASKS = N_TASKS_ROW * MR;
 
     const int lane = threadIdx.x & 31;
     ChromaConsts cc{};
-    if constexpr (N_CHROMA == 1) cc = chroma_consts<CT>(lane >= 16);
+    if constexpr (PAIRED && !BYTES && NCOMP > 1) cc = chroma_consts<CT>(lane >= 16);
     const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
     uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
@@ -588,14 +656,16 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             int comp, bv = 0, bxl = lane; // component, block row inside the MCU row, block column inside the tile
             bool full = true;
             if (task < N_FULL) {
-                comp = (NCOMP == 4 && task >= VS) ? 3 : 0;
-                bv = (NCOMP == 4 && task >= VS) ? task - VS : task;
-            } else if (N_CHROMA == 1) {
-                comp = lane < 16 ? 1 : 2;
+                comp = Fmt<CT>::full_comp(task >= VS ? 1 : 0);
+                bv = task >= VS ? task - VS : task;
+            } else if (PAIRED) {
+                const int ci = 2 * (task - N_FULL) + (lane >> 4);
+                if (ci >= Fmt<CT>::NSUB) continue; // an odd number of 1x1 components: the last task runs half empty
+                comp = Fmt<CT>::sub_comp(ci);
                 bxl = lane & 15;
                 full = false;
             } else {
-                comp = 1 + (task - N_FULL);
+                comp = Fmt<CT>::sub_comp(task - N_FULL);
                 full = !SUB;
             }
             const int H = full ? HS : 1, V = full ? VS : 1;
@@ -607,7 +677,11 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             int v[64];
             if constexpr (CT == JPGB_LUMA) {
                 load_block<CT, ROLE_RAW, 1, 1>(base, PITCH, v);
-            } else if constexpr (N_CHROMA == 1) {
+            } else if constexpr (BYTES) {
+                const unsigned xorv = CT == JPGB_CMYK ? 0xFFu : 0u; // 255 - c, image_buffer.rs:247-256
+                if (full) load_block_bytes<BPP, 1, 1>(base, PITCH, v, (unsigned)comp, xorv);
+                else load_block_bytes<BPP, HS, VS>(base, PITCH, v, (unsigned)comp, xorv);
+            } else if constexpr (PAIRED) {
                 if (task >= N_FULL) load_block<CT, ROLE_CBCR, HS, VS>(base, PITCH, v, &cc); // lanes 0..15 Cb, 16..31 Cr
                 else if (comp == 0) load_block<CT, ROLE_Y, 1, 1>(base, PITCH, v);
                 else load_block<CT, ROLE_K, 1, 1>(base, PITCH, v);
@@ -744,6 +818,9 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
         case JPGB_BGR: return launch_fast_ct<JPGB_BGR>(p, block, smem, stream);
         case JPGB_BGRA: return launch_fast_ct<JPGB_BGRA>(p, block, smem, stream);
         case JPGB_CMYK_AS_YCCK: return launch_fast_ct<JPGB_CMYK_AS_YCCK>(p, block, smem, stream);
+        case JPGB_YCBCR: return launch_fast_ct<JPGB_YCBCR>(p, block, smem, stream);
+        case JPGB_YCCK: return launch_fast_ct<JPGB_YCCK>(p, block, smem, stream);
+        case JPGB_CMYK: return launch_fast_ct<JPGB_CMYK>(p, block, smem, stream);
         default: break;
         }
     }

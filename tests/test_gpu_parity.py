@@ -84,7 +84,9 @@ def test_stage_a_coefficients(color, sampling, optimize):
 def test_generic_and_fast_stage_a_kernels_agree(monkeypatch):
     """Formats served by the fast kernel must also be exact through the generic one (and vice versa)."""
     for color, sampling in (("rgb", (2, 2)), ("bgr", (2, 1)), ("rgba", (1, 2)), ("bgra", (1, 1)), ("luma", (1, 1)),
-                            ("cmyk_as_ycck", (2, 2)), ("cmyk_as_ycck", (1, 1))):
+                            ("cmyk_as_ycck", (2, 2)), ("cmyk_as_ycck", (1, 1)), ("ycbcr", (2, 2)), ("ycbcr", (1, 1)), ("ycbcr", (2, 1)),
+                            ("ycbcr", (1, 2)), ("ycck", (2, 2)), ("ycck", (1, 1)), ("ycck", (2, 1)), ("cmyk", (2, 2)), ("cmyk", (1, 1)),
+                            ("cmyk", (2, 1)), ("cmyk", (1, 2))):
         cfg = dict(quality=83, sampling=sampling)
         img = _img(color, 333, 77, seed=11)
         want = oracle_encode(img, 333, 77, color, cfg)
