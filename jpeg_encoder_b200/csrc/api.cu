@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/jpegenc_b200.h"
@@ -100,6 +101,7 @@ struct jpgb_encoder {
     bool stage_busy[2] = {};
     int out_slot = 0; // which of out / out2 the next encode_device writes
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_slice;
     cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_enc[2] = {};
     bool timing = false;
     cudaEvent_t ev[JPGB_N_STAGES + 1][2] = {};
@@ -189,7 +191,8 @@ int validate_and_plan(jpgb_encoder *enc, const jpgb_params *p, size_t len_each, 
 // `given_hist` (strips with optimized tables): the symbol histogram of the *whole* image, [table][dc|ac][257],
 // used instead of the one of these pixels.
 int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, size_t image_stride, uint32_t n,
-                  std::vector<uint64_t> &offsets, std::vector<uint64_t> *piece_offsets = nullptr, const uint32_t *given_hist = nullptr) {
+                  std::vector<uint64_t> &offsets, std::vector<uint64_t> *piece_offsets = nullptr, const uint32_t *given_hist = nullptr,
+                  bool coef_ready = false) {
     cudaStream_t st = enc->stream;
     DevPlan hp;
     plan.fill_device_plan(hp);
@@ -201,8 +204,8 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     const uint64_t n_segs = (uint64_t)plan.segs_per_image * n;
 
     CK(enc->coef.reserve(n_blocks * 128), "alloc coefficients");
-    // ---- stage A ----
-    {
+    // ---- stage A (unless the caller has already run it slice by slice behind the upload) ----
+    if (!coef_ready) {
         StageTimer t(enc, 0);
         ap.pixels = d_pixels;
         ap.coef = enc->coef.as<int16_t>();
@@ -551,6 +554,25 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 // while the copy engine drains one, the host fills the other, so the DMA never waits for a page-locked bounce
 // inside the driver and the copy stays asynchronous.
 constexpr size_t kStageBytes = 8u << 20;
+// One core copies ~10 GB/s into pinned memory, a fifth of what the link takes: large pieces are split over a few threads.
+void parallel_copy(void *dst, const uint8_t *src, size_t n) {
+    constexpr size_t kMinPerThread = 1u << 20;
+    unsigned threads = (unsigned)std::min<size_t>(4, n / kMinPerThread);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw && threads > hw) threads = hw;
+    if (threads <= 1) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    const size_t part = ((n / threads) + 63) & ~(size_t)63;
+    std::thread workers[3];
+    for (unsigned t = 1; t < threads; ++t) {
+        const size_t lo = t * part, hi = t + 1 == threads ? n : std::min(n, lo + part);
+        workers[t - 1] = std::thread([=] { if (lo < hi) std::memcpy(static_cast<uint8_t *>(dst) + lo, src + lo, hi - lo); });
+    }
+    std::memcpy(dst, src, std::min(part, n));
+    for (unsigned t = 1; t < threads; ++t) workers[t - 1].join();
+}
 cudaError_t upload_host(jpgb_encoder *enc, void *d_dst, const uint8_t *src, size_t bytes, cudaStream_t s) {
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
@@ -565,7 +587,7 @@ cudaError_t upload_host(jpgb_encoder *enc, void *d_dst, const uint8_t *src, size
             e = cudaEventSynchronize(enc->ev_stage[b]);
             if (e != cudaSuccess) return e;
         }
-        std::memcpy(enc->h_stage[b].p, src + off, n);
+        parallel_copy(enc->h_stage[b].p, src + off, n);
         e = cudaMemcpyAsync(static_cast<uint8_t *>(d_dst) + off, enc->h_stage[b].p, n, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return e;
         e = cudaEventRecord(enc->ev_stage[b], s);
@@ -592,6 +614,51 @@ int encode_host_pipelined(jpgb_encoder *enc, const Plan &plan, const uint8_t *co
     CK(enc->h_out.reserve(std::max<size_t>(img_bytes * n / 3, 1 << 20)), "alloc pinned output");
     offsets.assign(1, 0);
     cudaStream_t st = enc->stream;
+
+    // One large image: the upload dominates (3 B/pixel over PCIe against ~1 ms of device work), so the image is cut into
+    // slices of whole MCU rows and the colour+DCT kernel runs on slice k while slice k + 1 is still on the link.
+    if (n == 1 && !plan.planar && img_bytes >= (48u << 20)) {
+        const size_t row_bytes = (size_t)plan.p.width * plan.bpp;
+        const uint32_t mcu_px = 8 * plan.vmax;
+        uint32_t rows_per_slice = (uint32_t)std::max<size_t>(1, (32u << 20) / (row_bytes * mcu_px)); // in MCU rows, ~32 MB
+        rows_per_slice = (rows_per_slice + 3) & ~3u; // whole warp tiles (up to four MCU rows each)
+        const uint32_t n_slices = (plan.mcu_rows + rows_per_slice - 1) / rows_per_slice;
+        CK(enc->pixels.reserve(stride), "alloc pixels");
+        CK(enc->coef.reserve(plan.blocks_per_image * 128), "alloc coefficients");
+        while (enc->ev_slice.size() < n_slices) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "create event");
+            enc->ev_slice.push_back(e);
+        }
+        StageAParams ap;
+        plan.fill_stage_a(ap);
+        for (uint32_t k = 0; k < n_slices; ++k) { // all uploads are queued first: the link never idles
+            const size_t r0 = (size_t)k * rows_per_slice * mcu_px, r1 = std::min<size_t>(plan.p.height, r0 + (size_t)rows_per_slice * mcu_px);
+            CK(upload_host(enc, enc->pixels.as<uint8_t>() + r0 * row_bytes, pixels[0] + r0 * row_bytes, (r1 - r0) * row_bytes, enc->s_h2d), "upload slice");
+            CK(cudaEventRecord(enc->ev_slice[k], enc->s_h2d), "record slice");
+        }
+        for (uint32_t k = 0; k < n_slices; ++k) {
+            const size_t r0 = (size_t)k * rows_per_slice * mcu_px, r1 = std::min<size_t>(plan.p.height, r0 + (size_t)rows_per_slice * mcu_px);
+            StageAParams sp = ap;
+            sp.pixels = enc->pixels.as<uint8_t>() + r0 * row_bytes;
+            sp.coef = enc->coef.as<int16_t>();
+            sp.image_stride = stride;
+            sp.height = (int)(r1 - r0);
+            sp.mcu_row0 = (int)(k * rows_per_slice);
+            sp.mcu_rows = (int)std::min<uint32_t>(rows_per_slice, plan.mcu_rows - k * rows_per_slice);
+            CK(cudaStreamWaitEvent(st, enc->ev_slice[k], 0), "wait slice");
+            CK(launch_stage_a(sp, 1, st), "stage A launch");
+            enc->launches += 1;
+        }
+        std::vector<uint64_t> off;
+        const int rc = encode_device(enc, plan, enc->pixels.as<uint8_t>(), stride, 1, off, nullptr, nullptr, true);
+        if (rc != JPGB_OK) return rc;
+        CK(enc->h_out.reserve(std::max<size_t>(off[1], 1 << 20)), "alloc pinned output");
+        CK(cudaMemcpyAsync(enc->h_out.p, enc->out.p, off[1], cudaMemcpyDeviceToHost, st), "download file");
+        CK(cudaStreamSynchronize(st), "download sync");
+        offsets.push_back(off[1]);
+        return JPGB_OK;
+    }
 
     auto upload = [&](uint32_t c) -> cudaError_t {
         DevBuf &px = (c & 1) ? enc->pixels2 : enc->pixels;
@@ -748,6 +815,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    for (cudaEvent_t ev : e->ev_slice) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);

@@ -58,6 +58,7 @@ struct StageAParams {
     // them, block = (mcu * bpu + slot). mcu_order = 0: per component the raster of its TRUE grid (comp_tw x comp_th,
     // the one encode_blocks walks), components back to back; blocks of the MCU padding are not stored.
     int mcu_order, bpu;
+    int mcu_row0;          // a horizontal slice of the image: its first MCU row inside the whole image (destination rows are global)
     int slot_base[4];      // first slot of the component inside the MCU (mcu_order)
     int comp_tw[4], comp_th[4];
     // per warp task inside a group: component and block position inside the MCU

@@ -198,10 +198,11 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const __grid_constant__ St
             dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
 
         size_t blk = (size_t)img * p.blocks_per_image;
+        const int gy = mcu_y + p.mcu_row0; // MCU row inside the whole image (this launch may cover a slice of it)
         if (p.mcu_order) { // the order the interleaved scan codes them (encoder.rs:747-791)
-            blk += ((size_t)mcu_y * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * p.comp_h[comp] + bh;
+            blk += ((size_t)gy * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * p.comp_h[comp] + bh;
         } else {           // raster of the component's true grid (encoder.rs:1012-1031); MCU padding blocks are not stored
-            const int by = mcu_y * p.comp_v[comp] + bv, bx = mcu_x * p.comp_h[comp] + bh;
+            const int by = gy * p.comp_v[comp] + bv, bx = mcu_x * p.comp_h[comp] + bh;
             if (bx >= p.comp_tw[comp] || by >= p.comp_th[comp]) continue;
             blk += p.comp_off[comp] + (size_t)by * p.comp_tw[comp] + bx;
         }
@@ -671,7 +672,8 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             const int H = full ? HS : 1, V = full ? VS : 1;
             const int bx = mcu_x0 * H + bxl;
             // blocks of the MCU padding exist only in the MCU-ordered layout (the interleaved scan codes them)
-            if (p.mcu_order ? bx >= p.comp_pw[comp] : (bx >= p.comp_tw[comp] || mcu_y * V + bv >= p.comp_th[comp])) continue;
+            const int gy = mcu_y + p.mcu_row0; // MCU row inside the whole image (this launch may cover a slice of it)
+            if (p.mcu_order ? bx >= p.comp_pw[comp] : (bx >= p.comp_tw[comp] || gy * V + bv >= p.comp_th[comp])) continue;
             const uint8_t *base = full ? mtile + (bv * 8) * PITCH + bxl * 8 * BPP : mtile + bxl * 8 * HS * BPP;
 
             int v[64];
@@ -701,9 +703,9 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
             size_t blk = (size_t)img * p.blocks_per_image;
             if (p.mcu_order) { // H, V are 1 or 2 here: bx = mcu_x * H + bh
                 const int mcu_x = H == 2 ? bx >> 1 : bx, bh = H == 2 ? bx & 1 : 0;
-                blk += ((size_t)mcu_y * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * H + bh;
+                blk += ((size_t)gy * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * H + bh;
             } else {
-                blk += p.comp_off[comp] + (size_t)(mcu_y * V + bv) * p.comp_tw[comp] + bx;
+                blk += p.comp_off[comp] + (size_t)(gy * V + bv) * p.comp_tw[comp] + bx;
             }
             int16_t *dst = p.coef + blk * 64;
             if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
