@@ -804,57 +804,76 @@ __global__ void __launch_bounds__(128) scan_offsets_kernel(const __grid_constant
 }
 
 // ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
-// One thread per block; the coefficient buffer holds every component's true grid in raster order (optimized tables
-// always code non-interleaved), so the block in front is the DC predecessor. DC category of the chained difference
-// with no restart resets (Q17); AC run/size symbols per progressive band (runs restart per band), ZRL for
-// runs > 15, EOB when a band ends in zeros. Bins: [image][table][dc|ac][257]. One launch for the whole batch:
-// blockIdx.y walks the images, a CTA never straddles two of them.
+// One CTA per 256 consecutive blocks of one image, staged like a coding chunk (the coefficient buffer holds every
+// component's true grid in raster order -- optimized tables always code non-interleaved -- so the blocks are one
+// contiguous run and the block in front is the DC predecessor). Every thread walks the set bits of its block's
+// non-zero mask, band by band: AC run/size symbols (runs restart per band), ZRL through the marker trick of the coder,
+// EOB when a band ends in zeros; DC category of the chained difference with NO restart resets (Q17).
+// Bins: [image][table][dc|ac][257], collected per CTA in shared memory. One launch for the whole batch.
 __global__ void __launch_bounds__(256) histogram_kernel(const __grid_constant__ DevPlan P, const int16_t *coef, unsigned n_images, uint32_t *hist,
                                                         int bands, int per_band) {
     __shared__ unsigned sh[2 * 2 * 257];
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; // block inside the image
+    __shared__ __align__(16) int16_t blk[256 * kStageStride];
+    const int tid = threadIdx.x;
+    const unsigned long long g0 = (unsigned long long)blockIdx.x * 256; // first block of this CTA inside the image
+    const unsigned n_here = P.blocks_per_image - g0 < 256 ? (unsigned)(P.blocks_per_image - g0) : 256u;
     for (unsigned img = blockIdx.y; img < n_images; img += gridDim.y) {
-        for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x) sh[i] = 0;
+        for (int i = tid; i < 2 * 2 * 257; i += 256) sh[i] = 0;
+        const int16_t *src = coef + ((unsigned long long)img * P.blocks_per_image + g0) * 64;
+        {
+            const unsigned pieces = n_here * 8;
+            const char *g = reinterpret_cast<const char *>(src) + (size_t)tid * 16;
+            const unsigned d = (unsigned)__cvta_generic_to_shared(blk) + (tid >> 3) * (kStageStride * 2) + (tid & 7) * 16;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((unsigned)(tid + k * 256) < pieces)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * 32 * (kStageStride * 2)), "l"(g + k * 256 * 16) : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
         __syncthreads();
-        if (g < P.blocks_per_image) {
+        if ((unsigned)tid < n_here) {
+            const unsigned long long g = g0 + tid;
             int comp = 0;
             while (comp + 1 < P.n_groups && g >= P.groups[comp + 1].block_base) ++comp;
-            const int16_t *blk = coef + ((unsigned long long)img * P.blocks_per_image + g) * 64;
-            const int prev = g > P.groups[comp].block_base ? (int)blk[-64] : 0;
+            const int16_t *mine = blk + tid * kStageStride;
+            const uint4 *m4 = reinterpret_cast<const uint4 *>(mine);
+            unsigned m_lo = 0, m_hi = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint4 q = m4[w];
+                unsigned byte = __dp2a_lo(nonzero16x2(q.x), 0x0201u, 0u);
+                byte = __dp2a_lo(nonzero16x2(q.y), 0x0804u, byte);
+                byte = __dp2a_lo(nonzero16x2(q.z), 0x2010u, byte);
+                byte = __dp2a_lo(nonzero16x2(q.w), 0x8040u, byte);
+                if (w < 4) m_lo |= byte << (8 * w);
+                else m_hi |= byte << (8 * (w - 4));
+            }
+            const unsigned long long m_all = (((unsigned long long)m_hi << 32) | m_lo) & ~1ull;
+            const int prev = g > P.groups[comp].block_base ? (tid > 0 ? (int)mine[-kStageStride] : (int)__ldg(src - 64)) : 0;
             unsigned *h = sh + P.comp_tbl[comp] * 2 * 257;
-            const int diff = (int)(int16_t)(blk[0] - prev);
+            const int diff = (int)(int16_t)(mine[0] - prev);
             atomicAdd(h + (32 - __clz(diff < 0 ? -diff : diff)), 1u);
             unsigned *ha = h + 257;
-            const uint4 *src = reinterpret_cast<const uint4 *>(blk);
-            int run = 0, band = 0, band_end = bands == 1 ? 64 : per_band; // band b covers [max(b*per,1), (b+1)*per), last to 64
-            for (int w = 0; w < 8; ++w) {
-                const uint4 q = __ldg(src + w);
-                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = w * 8 + j;
-                    if (k == 0) continue;
-                    if (k == band_end) { // band boundary: close the previous band
-                        if (run > 0) atomicAdd(ha, 1u);
-                        run = 0;
-                        ++band;
-                        band_end = band == bands - 1 ? 64 : (band + 1) * per_band;
-                    }
-                    const int c = (int)(int16_t)(words[j >> 1] >> ((j & 1) * 16));
-                    if (c == 0) {
-                        ++run;
-                    } else {
-                        for (; run > 15; run -= 16) atomicAdd(ha + 0xF0, 1u);
-                        atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
-                        run = 0;
-                    }
+            for (int b = 0; b < bands; ++b) { // band b covers [max(b * per, 1), (b + 1) * per), the last one to 63
+                const int first_ac = b == 0 ? 1 : b * per_band, se = b == bands - 1 ? 63 : (b + 1) * per_band - 1;
+                if (se < first_ac) continue; // the empty first band of 34..64 scans
+                unsigned long long m = m_all & (~0ull << first_ac) & (~0ull >> (63 - se));
+                m |= zrl_markers(m, first_ac);
+                int next = first_ac;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int c = mine[k];
+                    const int run = k - next; // <= 15 thanks to the markers; a marker is a zero: size 0 -> symbol 0xF0
+                    next = k + 1;
+                    atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
                 }
+                if (next <= se) atomicAdd(ha, 1u);
             }
-            if (run > 0) atomicAdd(ha, 1u);
         }
         __syncthreads();
         uint32_t *dst = hist + (size_t)img * (2 * 2 * 257);
-        for (int i = threadIdx.x; i < 2 * 2 * 257; i += blockDim.x)
+        for (int i = tid; i < 2 * 2 * 257; i += 256)
             if (sh[i]) atomicAdd(dst + i, sh[i]);
         __syncthreads();
     }
