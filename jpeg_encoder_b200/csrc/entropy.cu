@@ -110,19 +110,19 @@ constexpr int kAsmWordsProg = 3072; // progressive: words of the chunk assembly 
 // zeros that end such a group of 16: start of the run + 15, + 31, + 47.
 __device__ __forceinline__ unsigned long long zrl_markers(unsigned long long m, int first_ac) {
     const unsigned long long z = m | (1ull << (first_ac - 1)); // the position in front of the band ends "run 0"
-    unsigned long long s = z; // bit j: z has a set bit in [j - 15, j]
+    // s16 / s32 / s48: bit p is set when z has a set bit among the 16 / 32 / 48 positions p, p - 1, ...
+    unsigned long long s = z;
     s |= s << 1;
     s |= s << 2;
     s |= s << 4;
-    s |= s << 8;
-    unsigned long long need = m & ~(s << 1); // non-zeros with 16 or more zeros in front of them
-    unsigned long long marks = 0;
-    while (need) { // rare
-        const int k = __ffsll((long long)need) - 1;
-        need &= need - 1;
-        const int j = 63 - __clzll((long long)(z & ((1ull << k) - 1ull))); // the set bit in front of k
-        for (int t = j + 16; t < k; t += 16) marks |= 1ull << t;
-    }
+    const unsigned long long s16 = s | (s << 8);
+    const unsigned long long s32 = s16 | (s16 << 16);
+    const unsigned long long s48 = s32 | (s16 << 32);
+    // a zero exactly 16 / 32 / 48 positions behind the nearest set bit below it
+    unsigned long long marks = ((z << 16) & ~s16) | ((z << 32) & ~s32) | ((z << 48) & ~s48);
+    // ... and only in front of a non-zero coefficient (zeros at the end of the band become EOB, writer.rs:383-385)
+    const int top = 63 - __clzll((long long)m); // -1 when the band is empty: the shift below then clears everything
+    marks &= top > 0 ? (~0ull >> (64 - top)) : 0ull;
     return marks;
 }
 
@@ -398,6 +398,11 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
                 __syncthreads();
             }
 
+            if (j == 0) { // the next chunk's blocks on their way into L2 while this one is coded (thread 0 has already decoded it)
+                const ItemInfo &nx = items[(round & 1) ^ 1];
+                if (!nx.done && (unsigned)tid < nx.n_valid)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(b.coef + (nx.blk0 + tid) * 64));
+            }
             // ---- 3. code the visit of rank tid ----
             {
                 const int src = order[tid];
@@ -428,28 +433,23 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
                 const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += o;
             }
-            if (lane == 31) wsum[warp] = inc;
-            __syncthreads();
+            // sums of the other warps' visits: every warp adds them up itself (one REDUX each) instead of meeting at a barrier
             unsigned off = inc - myb, total = 0;
 #pragma unroll
             for (int w = 0; w < T / 32; ++w) {
-                const unsigned sw = wsum[w];
+                const unsigned sw = __reduce_add_sync(0xffffffffu, nbv[w * 32 + lane]);
                 if (w < warp) off += sw;
                 total += sw;
             }
             const unsigned total_words = (total + 31) >> 5;
             const unsigned long long ci = it.chunk_index0 + S.chunk_base;
+            // room in the pool: requested now, looked at only when the chunk is written out (the atomic's round trip
+            // overlaps the assembly)
+            const unsigned pool_units = (total_words + 3) >> 2; // 16-byte units
+            unsigned long long pool_at = 0;
             if (tid == 0) {
-                const unsigned units = (total_words + 3) >> 2; // 16-byte units
-                unsigned long long at = units ? atomicAdd(b.status + 5, (unsigned long long)units) : 0ull;
-                if (at + units > b.pool_cap) {
-                    atomicOr(b.status + 2, 4ull);
-                    at = ~0ull;
-                }
-                wsum[8] = (uint32_t)at;
-                wsum[9] = (uint32_t)(at >> 32);
+                if (pool_units) pool_at = atomicAdd(b.status + 5, (unsigned long long)pool_units);
                 b.chunk_bits[ci] = total;
-                b.chunk_pool[ci] = (uint32_t)at;
             }
             for (unsigned wb = 0; wb < total_words; wb += L::kAsmWords) { // one pass unless the chunk is larger than the buffer
                 const unsigned nwin = total_words - wb < (unsigned)L::kAsmWords ? total_words - wb : (unsigned)L::kAsmWords;
@@ -484,6 +484,15 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
                             }
                         }
                     }
+                }
+                if (tid == 0 && wb == 0) {
+                    if (pool_at + pool_units > b.pool_cap) {
+                        atomicOr(b.status + 2, 4ull);
+                        pool_at = ~0ull;
+                    }
+                    wsum[8] = (uint32_t)pool_at;
+                    wsum[9] = (uint32_t)(pool_at >> 32);
+                    b.chunk_pool[ci] = (uint32_t)pool_at;
                 }
                 __syncthreads();
                 const unsigned long long at = ((unsigned long long)wsum[9] << 32) | wsum[8];
