@@ -177,6 +177,33 @@ class ClockSampler:
                 "how": "nvidia-smi every 50 ms from the warm-up through the timed steps plus ~1 s of the same work un-timed; median of the upper half"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Host side of the end-to-end path: every rank's pinned staging memory and its copy threads should live on the
+    NUMA node its GPU hangs off, or the uploads of 8 ranks fight over the socket interconnect. Binds this process to
+    the CPUs of that node (first-touch then places the pinned pages there) and returns what it did for the JSON line."""
+    info = {"bound": False}
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        cpulist = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=cpulist, n_cpus=len(allowed))
+    except (OSError, ValueError, AttributeError) as e:
+        info["error"] = str(e)[:120]
+    return info
+
+
 # ---- the product arm ------------------------------------------------------------------------------
 def run_product(args):
     import torch
@@ -194,6 +221,7 @@ def run_product(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev_t = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"bound": False, "note": "single rank: not bound"}
 
     width, height, color, cfg, def_batch, desc = WORKLOADS[args.workload]
     cfg = resolve_cfg(cfg)
@@ -466,7 +494,7 @@ def run_product(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": total_frames * img_bytes,
                 "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "api": "jpgb_encode_batch_pinned (pinned host pixels -> host JPEG files; chunked upload/encode/download overlap)",
-                "h2d_link_gbs_measured": h2d_gbs, "h2d_gbs_in_e2e": batch * img_bytes * e2e_steps / e2e_s / 1e9,
+                "host_placement": numa, "h2d_link_gbs_measured": h2d_gbs, "h2d_gbs_in_e2e": batch * img_bytes * e2e_steps / e2e_s / 1e9,
                 "frac_of_link": (batch * img_bytes * e2e_steps / e2e_s / 1e9) / h2d_gbs,
                 "note": "end to end is bound by the host->device link (bpp bytes per pixel over PCIe): frac_of_link = h2d_gbs_in_e2e / h2d_link_gbs_measured (rank 0)",
                 "drop_in_call": {"api": "jpgb_encode_to_sink: one image per call, what Encoder::encode(&[u8]) binds (sink = the crate's JfifWrite::write_all)", "calls": n_calls, "unit": "megapixels/s",

@@ -70,6 +70,7 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
         const uint32_t m2 = __reduce_min_sync(0xffffffffu, lf2);
         if (m2 == kNone) break;
         const unsigned v2 = __reduce_max_sync(0xffffffffu, lf2 == m2 ? li2 : 0u);
+        __syncwarp(); // every lane has finished reading the frequencies of this round
         if (lane == 0) {
             S.freq[v1] = m1 + m2;
             S.freq[v2] = 0;
