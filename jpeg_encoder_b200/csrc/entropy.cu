@@ -581,7 +581,15 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant
         const unsigned long long h = b.huff_per_image ? img : 0;
         const unsigned n = b.hdr_len[h];
         const uint8_t *src = b.hdr + h * b.hdr_stride;
-        for (unsigned j = lane; j < n; j += 32) put_raw(b, pos + j, src[j]);
+        // the bytes (independent loads, several in flight), then the raw flags one 32-bit mask word at a time
+#pragma unroll 4
+        for (unsigned j = lane; j < n; j += 32) b.ustream[pos + j] = src[j];
+        const unsigned long long w0 = pos >> 5, w1 = (pos + n - 1) >> 5;
+        for (unsigned long long w = w0 + lane; w <= w1 && n; w += 32) {
+            const unsigned long long lo = w * 32 > pos ? w * 32 : pos, hi = (w + 1) * 32 < pos + n ? (w + 1) * 32 : pos + n; // [lo, hi) of this word
+            const unsigned bits = (unsigned)(hi - lo);
+            atomicOr(b.raw_mask + w, (bits == 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u)) << (unsigned)(lo & 31));
+        }
     }
     if (s == P.segs_per_image - 1 && P.has_eoi && lane == 0) {
         const unsigned long long end = b.segpos[g + 1];

@@ -15,13 +15,13 @@ namespace jpgb {
 namespace {
 
 constexpr int kSym = 257;      // 256 symbols + the reserved code point (src/encoder.rs:1092-1095)
-constexpr int kPerLane = 9;    // ceil(257 / 32): lane l owns symbols l, l + 32, ...
 constexpr unsigned kNone = 0xFFFFFFFFu;
 
 struct TableSmem {
     uint32_t freq[kSym + 31];
-    uint16_t root[kSym + 31];
-    uint8_t codesize[kSym + 31];
+    uint16_t root[kSym + 31], sym[kSym + 31]; // K.1 runs on the symbols that occur, packed to the front
+    uint8_t csz[kSym + 31];                   // code size of packed entry i
+    uint8_t codesize[kSym + 31];              // ... and of symbol s
     uint8_t values[256];
     uint8_t len[16];      // BITS after Figure K.3
     uint32_t n_values;
@@ -30,15 +30,13 @@ struct TableSmem {
     uint32_t first_code[17], first_pos[17];
 };
 
-// local minimum of a lane: the least non-zero frequency among its symbols, ties to the largest index
-__device__ __forceinline__ void lane_min(const uint32_t *freq, int lane, unsigned skip, uint32_t &f, unsigned &idx) {
+// local minimum of a lane: the least non-zero frequency among its entries, ties to the largest index
+__device__ __forceinline__ void lane_min(const uint32_t *freq, int lane, unsigned n, unsigned skip, uint32_t &f, unsigned &idx) {
     f = kNone;
     idx = kNone;
-#pragma unroll
-    for (int j = 0; j < kPerLane; ++j) {
-        const unsigned i = lane + 32 * j;
+    for (unsigned i = lane; i < n; i += 32) {
         const uint32_t v = freq[i];
-        if (i < kSym && i != skip && v != 0 && v <= f) {
+        if (i != skip && v != 0 && v <= f) {
             f = v;
             idx = i;
         }
@@ -49,15 +47,27 @@ __device__ __forceinline__ void lane_min(const uint32_t *freq, int lane, unsigne
 // ((code length + value size) << 27 | code << size) and the DHT segment; returns false if a code does not fit.
 __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int table_id, uint32_t *words, uint8_t *dht, uint32_t &dht_len) {
     const int lane = threadIdx.x & 31;
-    for (int i = lane; i < kSym + 31; i += 32) {
-        S.freq[i] = i < 256 ? freq_in[i] : (i == 256 ? 1u : 0u);
-        S.root[i] = (uint16_t)i;
-        S.codesize[i] = 0;
+    // Only symbols that occur take part in Figure K.1 (a zero frequency is never selected): they are packed to the
+    // front in symbol order, so "the largest index among equal frequencies" is still the largest symbol.
+    unsigned n = 0;
+    for (int base = 0; base < kSym + 31; base += 32) {
+        const int sym = base + lane;
+        const uint32_t f = sym < 256 ? freq_in[sym] : (sym == 256 ? 1u : 0u);
+        const unsigned have = __ballot_sync(0xffffffffu, f != 0);
+        if (f) {
+            const unsigned at = n + __popc(have & ((1u << lane) - 1u));
+            S.freq[at] = f;
+            S.sym[at] = (uint16_t)sym;
+            S.root[at] = (uint16_t)at;
+        }
+        if (sym < kSym + 31) S.codesize[sym] = 0;
+        n += __popc(have);
     }
+    for (int i = lane; i < kSym + 31; i += 32) S.csz[i] = 0;
     __syncwarp();
     uint32_t lf;
     unsigned li;
-    lane_min(S.freq, lane, kNone, lf, li);
+    lane_min(S.freq, lane, n, kNone, lf, li);
     bool ok = true;
     for (;;) { // Figure K.1
         const uint32_t m1 = __reduce_min_sync(0xffffffffu, lf);
@@ -66,7 +76,7 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
         // v2: the same rule over everything but v1; only v1's lane has to look again
         uint32_t lf2 = lf;
         unsigned li2 = li;
-        if ((v1 & 31) == (unsigned)lane) lane_min(S.freq, lane, v1, lf2, li2);
+        if ((v1 & 31) == (unsigned)lane) lane_min(S.freq, lane, n, v1, lf2, li2);
         const uint32_t m2 = __reduce_min_sync(0xffffffffu, lf2);
         if (m2 == kNone) break;
         const unsigned v2 = __reduce_max_sync(0xffffffffu, lf2 == m2 ? li2 : 0u);
@@ -75,23 +85,22 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
             S.freq[v1] = m1 + m2;
             S.freq[v2] = 0;
         }
-        // every member of both trees moves one level down; v2's tree joins v1's. A tree is named after the symbol
+        // every member of both trees moves one level down; v2's tree joins v1's. A tree is named after the entry
         // that holds its frequency, which is exactly how v1 and v2 were found.
-        const unsigned r1 = v1, r2 = v2;
-#pragma unroll
-        for (int j = 0; j < kPerLane; ++j) {
-            const unsigned i = lane + 32 * j;
+        for (unsigned i = lane; i < n; i += 32) {
             const unsigned r = S.root[i];
-            if (i < kSym && (r == r1 || r == r2)) {
-                const unsigned c = S.codesize[i] + 1u;
+            if (r == v1 || r == v2) {
+                const unsigned c = S.csz[i] + 1u;
                 if (c > 32) ok = false; // the reference panics on its fixed arrays
-                S.codesize[i] = (uint8_t)(c > 255 ? 255 : c);
-                S.root[i] = (uint16_t)r1;
+                S.csz[i] = (uint8_t)(c > 255 ? 255 : c);
+                S.root[i] = (uint16_t)v1;
             }
         }
         __syncwarp();
-        if ((v1 & 31) == (unsigned)lane || (v2 & 31) == (unsigned)lane) lane_min(S.freq, lane, kNone, lf, li);
+        if ((v1 & 31) == (unsigned)lane || (v2 & 31) == (unsigned)lane) lane_min(S.freq, lane, n, kNone, lf, li);
     }
+    for (unsigned i = lane; i < n; i += 32) S.codesize[S.sym[i]] = S.csz[i]; // back to symbol order
+    __syncwarp();
     ok = __all_sync(0xffffffffu, ok);
     if (!ok) return false;
 
@@ -148,8 +157,8 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
     // lookup: symbol values[k] gets the k-th code in order of length
     for (int i = lane; i < 256; i += 32) words[i] = 0; // a symbol without a code: only its value bits are written (Q18)
     __syncwarp();
-    const uint32_t n = S.n_values;
-    for (uint32_t k = lane; k < n; k += 32) {
+    const uint32_t nv = S.n_values;
+    for (uint32_t k = lane; k < nv; k += 32) {
         int l = 1;
         while (l < 16 && k >= S.first_pos[l] + S.len[l - 1]) ++l;
         const uint32_t code = S.first_code[l] + (k - S.first_pos[l]);
@@ -172,14 +181,14 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
     if (lane == 0) {
         dht[0] = 0xFF;
         dht[1] = 0xC4;
-        const uint32_t seg = 2 + 1 + 16 + n;
+        const uint32_t seg = 2 + 1 + 16 + nv;
         dht[2] = (uint8_t)(seg >> 8);
         dht[3] = (uint8_t)seg;
         dht[4] = (uint8_t)(((ac ? 1 : 0) << 4) | table_id);
-        dht_len = 5 + 16 + n;
+        dht_len = 5 + 16 + nv;
     }
     for (int i = lane; i < 16; i += 32) dht[5 + i] = S.len[i];
-    for (uint32_t i = lane; i < n; i += 32) dht[21 + i] = S.values[i];
+    for (uint32_t i = lane; i < nv; i += 32) dht[21 + i] = S.values[i];
     __syncwarp();
     return __all_sync(0xffffffffu, ok);
 }
