@@ -178,15 +178,13 @@ struct CoderSmem {
     static constexpr int kCoefBytes = T * kStageStride * 2;
     static constexpr int kAsmWords = FULL ? kCoefBytes / 4 : kAsmWordsProg; // FULL: the staged blocks are dead once coded -> reuse
     static constexpr int oAsm = FULL ? 0 : kCoefBytes;
-    static constexpr int oMask = kCoefBytes + (FULL ? 0 : kAsmWordsProg * 4);
-    static constexpr int oAc = oMask + T * 8;
+    // per visit: band mask (8 B), DC code word (4 B), table | valid (4 B) live in the 16 pad bytes behind its staged block
+    static constexpr int oAc = kCoefBytes + (FULL ? 0 : kAsmWordsProg * 4);
     static constexpr int oDc = oAc + 4096;  // AC tables: 2 x 256 x {code << size, length}
     static constexpr int oSlot = oDc + 256; // DC tables: 2 x 16 x {code << size, length}
     static constexpr int oBin = oSlot + 128; // per MCU slot: table | distance to the DC predecessor << 8 | first of its component << 16
     static constexpr int oNb = oBin + 256;
-    static constexpr int oFirst = oNb + T * 4;
-    static constexpr int oInfo = oFirst + T * 4;
-    static constexpr int oOrder = oInfo + T * 4;
+    static constexpr int oOrder = oNb + T * 4;
     static constexpr int oWsum = oOrder + T * 2;
     static constexpr int oItem = oWsum + 64;
     static constexpr int kBytes = oItem + 2 * 64; // two ItemInfo: the chunk being coded and the next one
@@ -210,14 +208,13 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem[];
     int16_t *coef = reinterpret_cast<int16_t *>(smem);
     uint32_t *asmbuf = reinterpret_cast<uint32_t *>(smem + L::oAsm);
-    unsigned long long *maskv = reinterpret_cast<unsigned long long *>(smem + L::oMask);
     uint2 *ac_tab = reinterpret_cast<uint2 *>(smem + L::oAc);
     uint2 *dc_tab = reinterpret_cast<uint2 *>(smem + L::oDc);
     uint32_t *slot_tab = reinterpret_cast<uint32_t *>(smem + L::oSlot);
     uint32_t *bin = reinterpret_cast<uint32_t *>(smem + L::oBin);
     uint32_t *nbv = reinterpret_cast<uint32_t *>(smem + L::oNb);
-    uint32_t *firstv = reinterpret_cast<uint32_t *>(smem + L::oFirst);
-    uint32_t *infov = reinterpret_cast<uint32_t *>(smem + L::oInfo);
+    // the 16 bytes behind the 128 coefficient bytes of visit v: {band mask lo, band mask hi, DC code word, table | valid << 8}
+    auto visit_meta = [&](int v) { return reinterpret_cast<uint4 *>(smem + v * (kStageStride * 2) + 128); };
     uint16_t *order = reinterpret_cast<uint16_t *>(smem + L::oOrder);
     uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + L::oWsum); // [0..7] warp sums, [8] pool offset of the chunk
     ItemInfo *items = reinterpret_cast<ItemInfo *>(smem + L::oItem);
@@ -372,9 +369,7 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
                     first = e.x | bits | e.y << 27;
                 }
             }
-            maskv[tid] = ((unsigned long long)m_hi << 32) | m_lo;
-            firstv[tid] = first;
-            infov[tid] = (unsigned)tbl | (valid ? 0x100u : 0u);
+            *visit_meta(tid) = make_uint4(m_lo, m_hi, first, (unsigned)tbl | (valid ? 0x100u : 0u));
             if (se > 0) {
                 const int nnz = __popc(m_lo) + __popc(m_hi); // <= 63
                 const unsigned rank = atomicAdd(&bin[nnz], 1u);
@@ -406,14 +401,14 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
             // ---- 3. code the visit of rank tid ----
             {
                 const int src = order[tid];
-                const unsigned inf = infov[src];
+                const uint4 meta = *visit_meta(src);
+                const unsigned inf = meta.w;
                 unsigned nb = 0;
                 if (inf & 0x100u) {
-                    const unsigned long long mask = maskv[src];
-                    const uint32_t dc_code = firstv[src];
+                    const uint32_t dc_code = meta.z;
                     BitSink<T> sink(scratch, src);
                     sink.put(dc_code & kCodeBits, (int)(dc_code >> 27));
-                    if (se > 0) code_nonzeros<T>((unsigned)mask, (unsigned)(mask >> 32), first_ac, se, coef + src * kStageStride, ac_tab + (inf & 0xFF) * 256, sink);
+                    if (se > 0) code_nonzeros<T>(meta.x, meta.y, first_ac, se, coef + src * kStageStride, ac_tab + (inf & 0xFF) * 256, sink);
                     nb = sink.finish();
                 }
                 nbv[src] = nb;
