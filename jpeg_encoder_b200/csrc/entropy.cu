@@ -132,7 +132,7 @@ __device__ __forceinline__ unsigned long long zrl_markers(unsigned long long m, 
 // coefficient, or a ZRL marker (zrl_markers): a zero 15 positions after the start of its run, for which the same
 // arithmetic yields the symbol 0xF0 with no value bits (writer.rs:369-373), so the loop has no ZRL branch.
 template <int BASE, int T>
-__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint2 *__restrict__ tab, BitSink<T> &sink) {
+__device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shared, const uint32_t *__restrict__ tab, BitSink<T> &sink) {
 #pragma unroll 1
     while (m) {
         int p;
@@ -148,20 +148,20 @@ __device__ __forceinline__ void code_half(unsigned m, int &next, unsigned c_shar
         int size;
         uint32_t bits;
         value_code(v, size, bits);
-        const uint2 e = (tab + run * 16)[size]; // .x = code << size, .y = code length + size
-        sink.put(e.x | bits, (int)e.y);
+        const uint32_t e = (tab + run * 16)[size]; // (code length + size) << 27 | code << size
+        sink.put((e & kCodeBits) | bits, (int)(e >> 27));
     }
 }
 template <int T>
 __device__ __forceinline__ void code_nonzeros(unsigned lo_rev, unsigned hi_rev, int first_ac, int se, const int16_t *__restrict__ c,
-                                              const uint2 *__restrict__ tab, BitSink<T> &sink) {
+                                              const uint32_t *__restrict__ tab, BitSink<T> &sink) {
     int next = first_ac;
     const unsigned c_shared = (unsigned)__cvta_generic_to_shared(c);
     code_half<0, T>(lo_rev, next, c_shared, tab, sink);
     code_half<32, T>(hi_rev, next, c_shared, tab, sink);
     if (next <= se) { // the band ends in zeros: EOB (writer.rs:383-385)
-        const uint2 e = tab[0];
-        sink.put(e.x, (int)e.y);
+        const uint32_t e = tab[0];
+        sink.put(e & kCodeBits, (int)(e >> 27));
     }
 }
 
@@ -180,7 +180,7 @@ struct CoderSmem {
     static constexpr int oAsm = FULL ? 0 : kCoefBytes;
     // per visit: band mask (8 B), DC code word (4 B), table | valid (4 B) live in the 16 pad bytes behind its staged block
     static constexpr int oAc = kCoefBytes + (FULL ? 0 : kAsmWordsProg * 4);
-    static constexpr int oDc = oAc + 4096;  // AC tables: 2 x 256 x {code << size, length}
+    static constexpr int oDc = oAc + 2048;  // AC tables: 2 x 256 packed words
     static constexpr int oSlot = oDc + 256; // DC tables: 2 x 16 x {code << size, length}
     static constexpr int oBin = oSlot + 128; // per MCU slot: table | distance to the DC predecessor << 8 | first of its component << 16
     static constexpr int oNb = oBin + 256;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem[];
     int16_t *coef = reinterpret_cast<int16_t *>(smem);
     uint32_t *asmbuf = reinterpret_cast<uint32_t *>(smem + L::oAsm);
-    uint2 *ac_tab = reinterpret_cast<uint2 *>(smem + L::oAc);
+    uint32_t *ac_tab = reinterpret_cast<uint32_t *>(smem + L::oAc);
     uint2 *dc_tab = reinterpret_cast<uint2 *>(smem + L::oDc);
     uint32_t *slot_tab = reinterpret_cast<uint32_t *>(smem + L::oSlot);
     uint32_t *bin = reinterpret_cast<uint32_t *>(smem + L::oBin);
@@ -286,8 +286,7 @@ __global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant_
         if (want_tab != tab_img) {
             const uint32_t *set = b.huff + (size_t)want_tab * kHuffWordsPerImage;
             for (int i = tid; i < 512; i += T) { // table 0 / 1, AC
-                const uint32_t e = __ldg(set + (i >> 8) * 512 + 256 + (i & 255));
-                ac_tab[i] = make_uint2(e & kCodeBits, e >> 27);
+                ac_tab[i] = __ldg(set + (i >> 8) * 512 + 256 + (i & 255));
             }
             if (tid < 32) { // DC categories 0..15
                 const uint32_t e = __ldg(set + (tid >> 4) * 512 + (tid & 15));
