@@ -597,62 +597,77 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant
 // last stream word of a chunk are shared with its neighbours and are merged with atomicOr (the stream is
 // zero-initialised); words in between are owned and stored. The warp of a segment's first chunk also writes the
 // pad bits of finalize_bit_buffer behind the segment's last bit (writer.rs:138-145: ones up to the byte boundary).
-__global__ void __launch_bounds__(256) place_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_chunks) {
+__global__ void __launch_bounds__(256) place_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_chunks,
+                                                           const unsigned per_warp) {
     if (!stream_fits(b) || (b.status[2] & 4ull)) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     uint32_t *stream = reinterpret_cast<uint32_t *>(b.ustream);
-    for (unsigned long long c = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
-        const unsigned long long img = c / P.chunks_per_image;
-        const unsigned r = (unsigned)(c - img * P.chunks_per_image);
-        const int k = find_scan_by_chunk(P, r);
-        const DevScan &S = P.scans[k];
-        const DevGroup &G = P.groups[k % P.n_groups];
-        unsigned seg, q;
-        divmod(r - S.chunk_base, G.div_cps, seg, q);
-        const unsigned bits = b.chunk_bits[c];
-        if (bits == 0 && q != 0) continue;
-        const unsigned long long seg_first = b.chunk_bitpos[c - q];
-        const unsigned long long rel_bits = b.chunk_bitpos[c] - seg_first;
-        const unsigned long long data_byte = b.segpos[img * P.segs_per_image + S.seg_base + seg] + lead_len(b, P, img, k, seg);
-        if (q == 0 && lane == 0) { // pad with ones up to the byte boundary behind the segment's last bit
-            const unsigned long long seg_bits = b.chunk_bitpos[c + G.cps] - seg_first;
-            const unsigned pad = (unsigned)(-(long long)seg_bits) & 7u;
-            if (pad) {
-                const unsigned long long pbit = data_byte * 8 + seg_bits;
-                const unsigned s2 = (unsigned)(pbit & 31); // pad never crosses a byte, hence never a word
-                atomicOr(stream + (pbit >> 5), __byte_perm(((1u << pad) - 1u) << (32 - s2 - pad), 0, 0x0123));
+    // A warp takes `per_warp` (1..32) consecutive chunks. First every lane works out where ONE of them goes (a chain of
+    // dependent loads: sizes, positions, segment start -- up to 32 chains in flight instead of one), then the warp
+    // copies them one after the other with all lanes. Small jobs take one chunk per warp: they need the warps.
+    for (unsigned long long c0 = (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * per_warp; c0 < n_chunks; c0 += warps * per_warp) {
+        const unsigned long long c = c0 + lane;
+        unsigned my_bits = 0, my_pool = 0;
+        unsigned long long my_bitpos = 0;
+        if ((unsigned)lane < per_warp && c < n_chunks) {
+            const unsigned long long img = c / P.chunks_per_image;
+            const unsigned r = (unsigned)(c - img * P.chunks_per_image);
+            const int k = find_scan_by_chunk(P, r);
+            const DevScan &S = P.scans[k];
+            const DevGroup &G = P.groups[k % P.n_groups];
+            unsigned seg, q;
+            divmod(r - S.chunk_base, G.div_cps, seg, q);
+            my_bits = b.chunk_bits[c];
+            if (my_bits != 0 || q == 0) {
+                const unsigned long long seg_first = b.chunk_bitpos[c - q];
+                const unsigned long long data_byte = b.segpos[img * P.segs_per_image + S.seg_base + seg] + lead_len(b, P, img, k, seg);
+                my_bitpos = data_byte * 8 + (b.chunk_bitpos[c] - seg_first);
+                if (my_bits) my_pool = b.chunk_pool[c];
+                if (q == 0) { // pad with ones up to the byte boundary behind the segment's last bit
+                    const unsigned long long seg_bits = b.chunk_bitpos[c + G.cps] - seg_first;
+                    const unsigned pad = (unsigned)(-(long long)seg_bits) & 7u;
+                    if (pad) {
+                        const unsigned long long pbit = data_byte * 8 + seg_bits;
+                        const unsigned s2 = (unsigned)(pbit & 31); // pad never crosses a byte, hence never a word
+                        atomicOr(stream + (pbit >> 5), __byte_perm(((1u << pad) - 1u) << (32 - s2 - pad), 0, 0x0123));
+                    }
+                }
             }
         }
-        if (bits == 0) continue;
-        const unsigned long long bitpos = data_byte * 8 + rel_bits;
-        const unsigned sft = (unsigned)(bitpos & 31);
-        uint32_t *dst = stream + (bitpos >> 5);
-        const uint32_t *src = b.pool + (size_t)b.chunk_pool[c] * 4;
-        const unsigned nw = (bits + 31) >> 5, ndw = (sft + bits + 31) >> 5;
-        const bool first_owned = sft == 0, last_owned = ((sft + bits) & 31) == 0;
-        uint32_t carry = 0; // source word in front of this step's first one
-        // 128 words per step: four independent, coalesced loads per lane are in flight together (the kernel is bound by
-        // load latency, not by bytes)
-        for (unsigned base = 0; base < ndw; base += 128) {
-            uint32_t cur[4];
+        unsigned todo = __ballot_sync(0xffffffffu, my_bits != 0);
+        while (todo) {
+            const int who = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned bits = __shfl_sync(0xffffffffu, my_bits, who);
+            const unsigned long long bitpos = __shfl_sync(0xffffffffu, my_bitpos, who);
+            const uint32_t *src = b.pool + (size_t)__shfl_sync(0xffffffffu, my_pool, who) * 4;
+            const unsigned sft = (unsigned)(bitpos & 31);
+            uint32_t *dst = stream + (bitpos >> 5);
+            const unsigned nw = (bits + 31) >> 5, ndw = (sft + bits + 31) >> 5;
+            const bool first_owned = sft == 0, last_owned = ((sft + bits) & 31) == 0;
+            uint32_t carry = 0; // source word in front of this step's first one
+            // 128 words per step: four independent, coalesced loads per lane are in flight together
+            for (unsigned base = 0; base < ndw; base += 128) {
+                uint32_t cur[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned d = base + 32 * u + lane;
-                cur[u] = d < nw ? __ldg(src + d) : 0u;
-            }
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned d = base + 32 * u + lane;
+                    cur[u] = d < nw ? __ldg(src + d) : 0u;
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned d = base + 32 * u + lane;
-                uint32_t prev = __shfl_up_sync(0xffffffffu, cur[u], 1);
-                if (lane == 0) prev = carry;
-                carry = __shfl_sync(0xffffffffu, cur[u], 31);
-                if (d < ndw) {
-                    const uint32_t val = sft ? __funnelshift_r(cur[u], prev, sft) : cur[u];
-                    const uint32_t be = __byte_perm(val, 0, 0x0123);
-                    const bool owned = (d > 0 || first_owned) && (d + 1 < ndw || last_owned);
-                    if (owned) dst[d] = be;
-                    else atomicOr(dst + d, be);
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned d = base + 32 * u + lane;
+                    uint32_t prev = __shfl_up_sync(0xffffffffu, cur[u], 1);
+                    if (lane == 0) prev = carry;
+                    carry = __shfl_sync(0xffffffffu, cur[u], 31);
+                    if (d < ndw) {
+                        const uint32_t val = sft ? __funnelshift_r(cur[u], prev, sft) : cur[u];
+                        const uint32_t be = __byte_perm(val, 0, 0x0123);
+                        const bool owned = (d > 0 || first_owned) && (d + 1 < ndw || last_owned);
+                        if (owned) dst[d] = be;
+                        else atomicOr(dst + d, be);
+                    }
                 }
             }
         }
@@ -992,8 +1007,10 @@ cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uin
 }
 cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long nc = (unsigned long long)hp.chunks_per_image * n;
-    const unsigned long long ctas = (nc + 7) / 8; // one warp per chunk, grid-stride beyond 64 K CTAs
-    place_chunks_kernel<<<(unsigned)(ctas < 65536 ? (ctas ? ctas : 1) : 65536), 256, 0, s>>>(b, hp, nc);
+    unsigned per_warp = 1; // chunks per warp: as many as leaves ~16 K warps of work
+    while (per_warp < 32 && nc / (per_warp * 2) >= 16384) per_warp *= 2;
+    const unsigned long long ctas = (nc + 8ull * per_warp - 1) / (8ull * per_warp); // grid-stride beyond 64 K CTAs
+    place_chunks_kernel<<<(unsigned)(ctas < 65536 ? (ctas ? ctas : 1) : 65536), 256, 0, s>>>(b, hp, nc, per_warp);
     return cudaGetLastError();
 }
 cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t s) {
