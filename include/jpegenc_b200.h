@@ -233,6 +233,9 @@ int jpgb_stage_a_device(jpgb_encoder *enc, const jpgb_params *p, const void *d_p
  * stage index: 0 = colour+DCT+quant kernel, 1 = histogram + table build (optimized only),
  * 2 = entropy coding into chunks + prefix sums, 3 = chunk placement (bit-granular copy into the stream),
  * 4 = byte stuffing + scatter, 5 = H2D, 6 = D2H. */
+/* Per-stage timing covers the device-resident entry points (jpgb_encode_batch_device, the strip calls, jpgb_encode_planar):
+ * with timing enabled they launch kernel by kernel between CUDA events instead of replaying their CUDA graph. The host
+ * entry points (jpgb_encode, jpgb_encode_batch*) run several such passes overlapped with copies and report no stages. */
 #define JPGB_N_STAGES 7
 void jpgb_encoder_set_timing(jpgb_encoder *enc, int enabled);
 int jpgb_encoder_last_timing(const jpgb_encoder *enc, float ms[JPGB_N_STAGES]);
@@ -250,6 +253,14 @@ int jpgb_build_header(const jpgb_params *p, uint8_t *buf, size_t cap, size_t *le
 /* HuffmanTable::new_optimized (Annex K.2, src/huffman.rs:99-221) as the host planner runs it on the
  * device histogram: code-length counts, values in code order, number of values. */
 int jpgb_optimized_huffman_table(const uint32_t freq[257], uint8_t length[16], uint8_t values[256], uint32_t *n_values);
+
+/* The same on the device (csrc/tables.cu: what the optimized encode path runs, one warp per table): `n` histograms of
+ * 257 counts each (host memory), every one built as an AC table (ac != 0) or a DC table. Per histogram: 16 length
+ * counts, up to 256 values, the number of values, and 256 kernel-format code words (0 where a symbol has no code is
+ * reported as its value size << 27). status[i] = JPGB_OK or JPGB_ERR_HUFFMAN. Test and diagnostics entry. */
+int jpgb_optimized_huffman_tables_device(jpgb_encoder *enc, const uint32_t *freq /* n * 257 */, uint32_t n, int ac,
+                                         uint8_t *lengths /* n * 16 */, uint8_t *values /* n * 256 */, uint32_t *n_values /* n */,
+                                         uint32_t *words /* n * 256 */, int *status /* n */);
 
 const char *jpgb_version(void);
 

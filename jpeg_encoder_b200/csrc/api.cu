@@ -1266,6 +1266,39 @@ int jpgb_optimized_huffman_table(const uint32_t freq[257], uint8_t length[16], u
     return JPGB_OK;
 }
 
+int jpgb_optimized_huffman_tables_device(jpgb_encoder *enc, const uint32_t *freq, uint32_t n, int ac, uint8_t *lengths, uint8_t *values,
+                                         uint32_t *n_values, uint32_t *words, int *status) {
+    if (!enc) return JPGB_ERR_BAD_PARAMS;
+    if (!freq || !lengths || !values || !n_values || !words || !status || n == 0) return fail(enc, JPGB_ERR_BAD_PARAMS, "null argument");
+    CK(cudaSetDevice(enc->device), "cudaSetDevice");
+    cudaStream_t st = enc->stream;
+    DevBuf d_hist, d_words, d_dht, d_len, d_bad;
+    auto release = [&] { d_hist.release(); d_words.release(); d_dht.release(); d_len.release(); d_bad.release(); };
+    std::vector<uint8_t> dht((size_t)n * 277);
+    std::vector<uint32_t> len(n), bad(n);
+    cudaError_t e = d_hist.reserve((size_t)n * 257 * 4);
+    if (e == cudaSuccess) e = d_words.reserve((size_t)n * 1024);
+    if (e == cudaSuccess) e = d_dht.reserve((size_t)n * 277);
+    if (e == cudaSuccess) e = d_len.reserve((size_t)n * 4);
+    if (e == cudaSuccess) e = d_bad.reserve((size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hist.p, freq, (size_t)n * 257 * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_build_single_tables(d_hist.as<uint32_t>(), n, ac, d_words.as<uint32_t>(), d_dht.as<uint8_t>(), d_len.as<uint32_t>(), d_bad.as<uint32_t>(), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(words, d_words.p, (size_t)n * 1024, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dht.data(), d_dht.p, dht.size(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(len.data(), d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bad.data(), d_bad.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    release();
+    if (e != cudaSuccess) return fail_cuda(enc, e, "device table build");
+    for (uint32_t i = 0; i < n; ++i) {
+        status[i] = bad[i] ? JPGB_ERR_HUFFMAN : JPGB_OK;
+        n_values[i] = bad[i] ? 0 : len[i] - 21;
+        std::memcpy(lengths + (size_t)i * 16, dht.data() + (size_t)i * 277 + 5, 16);
+        std::memcpy(values + (size_t)i * 256, dht.data() + (size_t)i * 277 + 21, 256);
+    }
+    return JPGB_OK;
+}
+
 const char *jpgb_version(void) { return "jpeg-encoder_b200 0.1 (sm_100a; parity target: jpeg-encoder 0.7.0)"; }
 
 } // extern "C"

@@ -189,10 +189,12 @@ bool HuffTable::set_optimized(const uint32_t freq_in[257]) {
         for (++codesize[v2]; others[v2] >= 0;) v2 = others[v2], ++codesize[v2];
     }
     uint8_t bits[33] = {0}; // Figure K.2
+    bool any = false;
     for (int i = 0; i < 257; ++i) {
         if (codesize[i] > 32) return false;
-        if (codesize[i]) ++bits[codesize[i]];
+        if (codesize[i]) ++bits[codesize[i]], any = true;
     }
+    if (!any) return false; // nothing but the reserved code point: the reference indexes out of bounds and panics
     int i = 32; // Figure K.3
     for (; i > 16; --i)
         while (bits[i] > 0) {

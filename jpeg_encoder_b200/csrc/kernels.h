@@ -81,6 +81,10 @@ cudaError_t launch_build_tables(const uint32_t *hist, int hist_per_image, int n_
                                 uint32_t head_len, const uint8_t *tail, uint32_t tail_len, uint8_t *hdr, uint32_t hdr_stride, uint32_t *hdr_len,
                                 unsigned long long *status, cudaStream_t stream);
 
+// one table per histogram, all of class `ac`: DHT segment bytes (5 + 16 + values, 277 apart), kernel words, error flags
+cudaError_t launch_build_single_tables(const uint32_t *hist, uint32_t n, int ac, uint32_t *words, uint8_t *dht, uint32_t *dht_len, uint32_t *bad,
+                                       cudaStream_t stream);
+
 // gather.cu -- a rank's pieces stored at their place in the assembled file (possibly in a peer GPU's memory)
 cudaError_t launch_place_pieces(const uint8_t *src, uint8_t *dst, unsigned long long dst_cap, const unsigned long long *table, unsigned world,
                                 unsigned rank, unsigned n_scans, unsigned long long *total_out, unsigned long long *status, cudaStream_t stream);

@@ -811,7 +811,7 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
     const size_t smem = (size_t)p.tile_pitch * p.tile_h_px * (p.planar ? p.ncomp : 1);
     const int n_tasks = p.groups * p.tasks_per_group;
     const int warps = n_tasks < 8 ? n_tasks : 8;
-    dim3 grid(p.tiles_per_row, p.mcu_rows, n_images), block(warps * 32);
+    dim3 grid(p.tiles_per_row, p.mcu_rows, 1), block(warps * 32);
     if (p.use_fast && !p.planar) {
         switch (p.color_type) {
         case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, block, smem, stream);
@@ -826,13 +826,21 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
         default: break;
         }
     }
+    // grid.z carries the image index and is limited to 65535: larger batches go in several launches
 #define JPGB_LAUNCH_A(CT)                                                                                        \
     case CT: {                                                                                                   \
         if (smem > 48 * 1024) {                                                                                  \
             cudaError_t e = cudaFuncSetAttribute(stage_a_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                      \
         }                                                                                                        \
-        stage_a_kernel<CT><<<grid, block, smem, stream>>>(p);                                                    \
+        for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {                                                      \
+            StageAParams q = p;                                                                                  \
+            q.pixels = p.pixels + (size_t)i0 * p.image_stride;                                                   \
+            q.coef = p.coef + (size_t)i0 * p.blocks_per_image * 64;                                              \
+            grid.z = n_images - i0 < 65535 ? n_images - i0 : 65535;                                              \
+            q.n_images = (int)grid.z;                                                                            \
+            stage_a_kernel<CT><<<grid, block, smem, stream>>>(q);                                                \
+        }                                                                                                        \
         break;                                                                                                   \
     }
     switch (p.planar ? kPlanar : p.color_type) {

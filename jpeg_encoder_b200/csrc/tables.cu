@@ -101,6 +101,7 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
     }
     for (unsigned i = lane; i < n; i += 32) S.codesize[S.sym[i]] = S.csz[i]; // back to symbol order
     __syncwarp();
+    if (n < 2) return false; // nothing but the reserved code point: no code at all (the reference indexes out of bounds and panics)
     ok = __all_sync(0xffffffffu, ok);
     if (!ok) return false;
 
@@ -228,7 +229,35 @@ __global__ void __launch_bounds__(128) build_tables_kernel(const uint32_t *__res
     if (threadIdx.x == 0) hdr_len[img] = pos + tail_len;
 }
 
+// test / diagnostics: one warp per histogram, every histogram on its own
+__global__ void __launch_bounds__(128) build_single_tables_kernel(const uint32_t *__restrict__ hist, unsigned n, int ac, uint32_t *words_out,
+                                                                  uint8_t *dht_out, uint32_t *dht_len_out, uint32_t *bad) {
+    __shared__ TableSmem S[4];
+    __shared__ uint8_t dht[4][5 + 16 + 256];
+    __shared__ uint32_t dht_len[4];
+    __shared__ uint32_t words[4][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    if (lane == 0) dht_len[warp] = 0;
+    __syncwarp();
+    const bool ok = build_one(S[warp], hist + (size_t)i * 257, ac != 0, 0, words[warp], dht[warp], dht_len[warp]);
+    __syncwarp();
+    if (lane == 0) {
+        bad[i] = ok ? 0u : 1u;
+        dht_len_out[i] = ok ? dht_len[warp] : 0u;
+    }
+    for (int k = lane; k < 256; k += 32) words_out[(size_t)i * 256 + k] = ok ? words[warp][k] : 0u;
+    for (unsigned k = lane; k < 5 + 16 + 256; k += 32) dht_out[(size_t)i * 277 + k] = ok && k < dht_len[warp] ? dht[warp][k] : 0;
+}
+
 } // namespace
+
+cudaError_t launch_build_single_tables(const uint32_t *hist, uint32_t n, int ac, uint32_t *words, uint8_t *dht, uint32_t *dht_len, uint32_t *bad,
+                                       cudaStream_t stream) {
+    build_single_tables_kernel<<<(n + 3) / 4, 128, 0, stream>>>(hist, n, ac, words, dht, dht_len, bad);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_build_tables(const uint32_t *hist, int hist_per_image, int n_tables, uint32_t n_images, uint32_t *huff, const uint8_t *head,
                                 uint32_t head_len, const uint8_t *tail, uint32_t tail_len, uint8_t *hdr, uint32_t hdr_stride, uint32_t *hdr_len,

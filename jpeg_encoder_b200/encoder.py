@@ -214,6 +214,8 @@ def load_library():
     l.jpgb_encoder_last_launch_count.restype = C.c_uint32
     l.jpgb_build_header.argtypes = [C.POINTER(_Params), u8p, C.c_size_t, C.POINTER(C.c_size_t)]
     l.jpgb_optimized_huffman_table.argtypes = [C.POINTER(C.c_uint32), u8p, u8p, C.POINTER(C.c_uint32)]
+    l.jpgb_optimized_huffman_tables_device.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32, C.c_int, u8p, u8p, C.POINTER(C.c_uint32),
+                                                       C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     l.jpgb_version.restype = C.c_char_p
     _lib = l
     return l

@@ -414,6 +414,91 @@ def test_strips_concatenate_to_the_whole_image(name, color, w, h, cfg, max_strip
     assert got == oracle_encode(img, w, h, color, cfg)
 
 
+def test_device_huffman_tables_equal_host_and_oracle():
+    """csrc/tables.cu (Annex K.2 on the device, what the optimized encode path runs) against the host planner and the
+    oracle on 600 histograms: skewed, flat, sparse, all-equal (every tie goes to the largest symbol), single-symbol,
+    Fibonacci-like (code lengths beyond 16 bits: Figure K.3) and beyond 32 bits (the reference panics: an error here)."""
+    import ctypes as C
+    import jpeg_encoder_b200 as je
+    dev = je.default_device(0)
+    lib = dev.lib
+    rng = np.random.default_rng(12)
+    # symbols 8-bit JPEG can produce: AC run/size with size 1..10 plus EOB (0x00) and ZRL (0xF0); DC categories 0..11
+    ac_syms = np.array([0x00, 0xF0] + [(r << 4) | z for r in range(16) for z in range(1, 11)])
+    dc_syms = np.arange(12)
+
+    def make_cases(syms):
+        cases = []
+        for i in range(280):
+            f = np.zeros(257, np.uint32)
+            k = int(rng.integers(1, len(syms) + 1))
+            idx = rng.choice(syms, k, replace=False)
+            r = rng.random()
+            if r < 0.5:
+                f[idx] = (rng.pareto(0.7, k) * 10 + 1).astype(np.uint32)
+            elif r < 0.75:
+                f[idx] = rng.integers(1, 50, k)
+            elif r < 0.9:
+                f[idx] = int(rng.integers(1, 4))  # all equal: nothing but ties
+            else:
+                f[idx] = rng.integers(1, 3, k)
+            cases.append(f)
+        for n_fib in (5, 10, 12, 20, 30, 40, 45):  # 30 and more force the length limiting; 40+ exceed 32 bits
+            if n_fib > len(syms):
+                continue
+            fib = np.zeros(257, np.uint32)
+            a, b = 1, 1
+            for i in range(n_fib):
+                fib[syms[i]] = min(a, 2 ** 32 - 1)
+                a, b = b, a + b
+            cases.append(fib)
+        for k in (0, 1, 2):  # no symbol at all / one / two
+            f = np.zeros(257, np.uint32)
+            f[syms[:k]] = 7
+            cases.append(f)
+        for f in cases:
+            f[256] = 1
+        return cases
+
+    total_bad = 0
+    for ac, syms in ((1, ac_syms), (0, dc_syms)):
+        cases = make_cases(syms)
+        n = len(cases)
+        flat = np.ascontiguousarray(np.stack(cases).astype(np.uint32))
+        lengths = (C.c_uint8 * (16 * n))()
+        values = (C.c_uint8 * (256 * n))()
+        nv = (C.c_uint32 * n)()
+        words = (C.c_uint32 * (256 * n))()
+        status = (C.c_int * n)()
+        rc = lib.jpgb_optimized_huffman_tables_device(dev.handle, flat.ctypes.data_as(C.POINTER(C.c_uint32)), n, ac, lengths, values, nv, words, status)
+        assert rc == 0, dev.last_error()
+        for i, f in enumerate(cases):
+            hl, hv, hn = (C.c_uint8 * 16)(), (C.c_uint8 * 256)(), C.c_uint32()
+            hrc = lib.jpgb_optimized_huffman_table(f.ctypes.data_as(C.POINTER(C.c_uint32)), hl, hv, C.byref(hn))
+            assert (hrc == 0) == (status[i] == 0), "case %d: host rc %d, device status %d" % (i, hrc, status[i])
+            if hrc != 0:  # a code longer than 32 bits: the reference panics
+                total_bad += 1
+                continue
+            assert list(lengths[16 * i:16 * i + 16]) == list(hl), "case %d lengths" % i
+            assert nv[i] == hn.value and list(values[256 * i:256 * i + nv[i]]) == list(hv)[:hn.value], "case %d values" % i
+            want_len, want_vals = orc.huffman_optimized(f.tolist())
+            assert list(hl) == want_len and list(hv)[:hn.value] == want_vals
+            # the code words the coding kernel reads: (length + size) << 27 | code << size, canonical codes in order of `values`
+            code, k = 0, 0
+            expect = {}
+            for bits in range(1, 17):
+                for _ in range(hl[bits - 1]):
+                    expect[hv[k]] = (bits, code)
+                    code += 1
+                    k += 1
+                code <<= 1
+            for sym in range(256 if ac else 16):
+                z = (sym & 15) if ac else sym
+                l, c = expect.get(sym, (0, 0))
+                assert words[256 * i + sym] == (((l + z) << 27) | (c << z)) & 0xFFFFFFFF, "case %d symbol %#x" % (i, sym)
+    assert total_bad >= 1
+
+
 def test_device_placed_gather_of_strip_pieces():
     """csrc/gather.cu on one GPU: the strips are encoded one after the other, and each time the placement kernel stores
     that strip's pieces at their final scan-major offsets inside the gather target, exactly as rank i of an N-GPU job

@@ -46,6 +46,26 @@ def ncu_raw(rep):
     return m, vals[hdr.index("Kernel Name")]
 
 
+def ncu_raw_all(rep):
+    """[(metrics, kernel name)] for every launch in the report"""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        if len(vals) != len(hdr):
+            continue
+        m = {}
+        for h, u, v in zip(hdr, units, vals):
+            if h in WANT or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
+                try:
+                    m[h] = {"value": float(v.replace(",", "")), "unit": u}
+                except ValueError:
+                    pass
+        res.append((m, vals[hdr.index("Kernel Name")]))
+    return res
+
+
 def mbytes(m, key):
     v = m[key]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v["unit"]]
@@ -85,32 +105,38 @@ def main():
                     " so only the SHARES are comparable with the live stage timers of the bench line)\n")
             for k, v in sorted(agg.items(), key=lambda x: -sum(x[1])):
                 f.write("%-50s n=%3d %10.1f us %5.1f%%  largest launch %8.1f us\n" % (k, len(v), sum(v), 100 * sum(v) / tot, max(v)))
-    # full captures
+    # full captures: one report with one launch of every dominant kernel (C3, 64 frames per launch)
     frames = 64
     alg = 1920 * 1080 * 3 + 128 * 48960
-    rep = os.path.join(SRC, tag + "_stage_a.ncu-rep")
+    rep = os.path.join(SRC, tag + "_full.ncu-rep")
     if os.path.exists(rep):
-        m, name = ncu_raw(rep)
-        tr = mbytes(m, "dram__bytes_read.sum") + mbytes(m, "dram__bytes_write.sum")
-        s = {"kernel": name, "command": "ncu --set full --clock-control none --import-source on -k regex:stage_a_warp -s 2 -c 1 "
-             "python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu", "frames_per_launch": frames,
-             "dram_bytes_per_launch": tr, "dram_bytes_per_frame": tr / frames, "algorithmic_bytes_per_frame": alg, "metrics": m,
-             "sass": "UTMALDG.3D (TMA), SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier), IDP.2A (colour), STG.E.ENL2.256 (stores): "
-                     "cuobjdump -sass jpeg_encoder_b200/build/stage_a.cu.o",
-             "note": "cold-cache single launch under ncu; the bench line's roofline.achieved uses the live CUDA-event time of the 1024-frame launch"}
-        json.dump(s, open(os.path.join(DST, out_tag + "_stage_a_ncu_summary.json"), "w"), indent=1)
-        json.dump({"workload": "c3", "dram_bytes_per_frame": tr / frames, "source": "profiles/%s_stage_a_ncu_summary.json" % out_tag},
-                  open(os.path.join(DST, "stage_a_traffic.json"), "w"), indent=1)
-    rep = os.path.join(SRC, tag + "_encode.ncu-rep")
-    if os.path.exists(rep):
-        m, name = ncu_raw(rep)
-        visits = frames * 48960
-        s = {"kernel": name, "command": "ncu --set full --clock-control none --import-source on -k regex:encode_visits -s 2 -c 1 "
-             "python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu", "frames_per_launch": frames, "visits_per_launch": visits,
-             "warp_instructions_per_warp_of_32_visits": m["smsp__inst_executed.sum"]["value"] / (visits / 32),
-             "algorithmic_bytes_per_frame": 128 * 48960, "metrics": m,
-             "note": "bound by the ALU pipe / instruction issue, not by HBM: see DESIGN.md section 4 (stage B)"}
-        json.dump(s, open(os.path.join(DST, out_tag + "_encode_ncu_summary.json"), "w"), indent=1)
+        cmd = ("ncu --set full --clock-control none --import-source on -k 'regex:stage_a_warp|encode_chunks|place_chunks|stuff_scatter|count_ff' "
+               "-s 10 -c 5 python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu --no-c5")
+        for m, name in ncu_raw_all(rep):
+            short = re.sub(r"\(.*", "", name).replace("jpgb::<unnamed>::", "").replace("void ", "").split("<")[0].strip()
+            rec = {"kernel": name, "command": cmd, "frames_per_launch": frames, "metrics": m,
+                   "note": "cold-cache single launch under ncu; live times are in the bench lines"}
+            if "dram__bytes_read.sum" in m:
+                tr = mbytes(m, "dram__bytes_read.sum") + mbytes(m, "dram__bytes_write.sum")
+                rec.update(dram_bytes_per_launch=tr, dram_bytes_per_frame=tr / frames)
+            if short.startswith("stage_a"):
+                rec["algorithmic_bytes_per_frame"] = alg
+                rec["sass"] = ("UTMALDG.3D (TMA), SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier), IDP.2A (colour), "
+                               "STG.E.ENL2.256 (stores): cuobjdump -sass jpeg_encoder_b200/build/stage_a.cu.o")
+                json.dump({"workload": "c3", "dram_bytes_per_frame": rec["dram_bytes_per_frame"],
+                           "source": "profiles/%s_stage_a_warp_kernel_ncu_summary.json" % out_tag}, open(os.path.join(DST, "stage_a_traffic.json"), "w"), indent=1)
+            if short.startswith("encode_chunks"):
+                visits = frames * 48960
+                rec["visits_per_launch"] = visits
+                rec["warp_instructions_per_32_visits"] = m["smsp__inst_executed.sum"]["value"] / (visits / 32)
+                rec["algorithmic_bytes_per_frame"] = 128 * 48960
+            json.dump(rec, open(os.path.join(DST, "%s_%s_ncu_summary.json" % (out_tag, short)), "w"), indent=1)
+    for w in ("c4a", "c4b"):
+        rep = os.path.join(SRC, "%s_stage_a_%s.ncu-rep" % (tag, w))
+        if os.path.exists(rep):
+            m, name = ncu_raw_all(rep)[0]
+            json.dump({"kernel": name, "workload": w, "metrics": m, "note": "one 8192x8192 image per launch, cold cache, under ncu"},
+                      open(os.path.join(DST, "%s_stage_a_%s_ncu_summary.json" % (out_tag, w)), "w"), indent=1)
 
 
 if __name__ == "__main__":
