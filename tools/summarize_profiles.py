@@ -113,7 +113,7 @@ def main():
         cmd = ("ncu --set full --clock-control none --import-source on -k 'regex:stage_a_warp|encode_chunks|place_chunks|stuff_scatter|count_ff' "
                "-s 10 -c 5 python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu --no-c5")
         for m, name in ncu_raw_all(rep):
-            short = re.sub(r"\(.*", "", name).replace("jpgb::<unnamed>::", "").replace("void ", "").split("<")[0].strip()
+            short = re.sub(r"\(.*", "", name).replace("void ", "").split("::")[-1].split("<")[0].strip()
             rec = {"kernel": name, "command": cmd, "frames_per_launch": frames, "metrics": m,
                    "note": "cold-cache single launch under ncu; live times are in the bench lines"}
             if "dram__bytes_read.sum" in m:
