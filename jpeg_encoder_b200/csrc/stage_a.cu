@@ -377,14 +377,14 @@ __device__ __forceinline__ void load_row(const uint8_t *row, int *s, const Chrom
             w[2 * i] = a.x;
             w[2 * i + 1] = a.y;
         }
-    } else if constexpr (BPP == 3 && SX == 2) {
+    } else if constexpr (BPP == 3) { // SX 2 or 4: the block's 8 * SX pixels are 48 / 96 bytes, 16-byte aligned
         const uint4 *r = reinterpret_cast<const uint4 *>(row);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < (NW + 3) / 4; ++i) {
             const uint4 a = r[i];
             w[4 * i] = a.x;
-            w[4 * i + 1] = a.y;
-            w[4 * i + 2] = a.z;
+            if (4 * i + 1 < NW) w[4 * i + 1] = a.y;
+            if (4 * i + 2 < NW) w[4 * i + 2] = a.z;
             if (4 * i + 3 < NW) w[4 * i + 3] = a.w;
         }
     } else if constexpr (BPP == 4 && SX == 1) {
@@ -397,10 +397,10 @@ __device__ __forceinline__ void load_row(const uint8_t *row, int *s, const Chrom
             w[4 * i + 2] = a.z;
             w[4 * i + 3] = a.w;
         }
-    } else { // BPP == 4, SX == 2: every other pixel word
+    } else { // BPP == 4, SX 2 or 4: every SX-th pixel word
         const uint32_t *r = reinterpret_cast<const uint32_t *>(row);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[2 * i] = r[2 * i];
+        for (int i = 0; i < 8; ++i) w[SX * i] = r[SX * i];
     }
     if constexpr (ROLE == ROLE_CBCR) chroma_row<CT, SX, NW>(w, s, *cc, std::make_integer_sequence<int, 8>{});
     else sample_row<CT, ROLE, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
@@ -434,11 +434,11 @@ __device__ __forceinline__ void load_row_bytes(const uint8_t *row, int *s, unsig
     } else if constexpr (BPP == 3) {
         const uint4 *r = reinterpret_cast<const uint4 *>(row);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < (NW + 3) / 4; ++i) {
             const uint4 a = r[i];
             w[4 * i] = a.x;
-            w[4 * i + 1] = a.y;
-            w[4 * i + 2] = a.z;
+            if (4 * i + 1 < NW) w[4 * i + 1] = a.y;
+            if (4 * i + 2 < NW) w[4 * i + 2] = a.z;
             if (4 * i + 3 < NW) w[4 * i + 3] = a.w;
         }
     } else if constexpr (SX == 1) {
@@ -451,10 +451,10 @@ __device__ __forceinline__ void load_row_bytes(const uint8_t *row, int *s, unsig
             w[4 * i + 2] = a.z;
             w[4 * i + 3] = a.w;
         }
-    } else { // 4 bytes per pixel, every other pixel
+    } else { // 4 bytes per pixel, every SX-th pixel
         const uint32_t *r = reinterpret_cast<const uint32_t *>(row);
 #pragma unroll
-        for (int i = 0; i < NW; ++i) w[i] = (i & 1) ? 0u : r[i];
+        for (int i = 0; i < NW; ++i) w[i] = (i % SX) ? 0u : r[i];
     }
     byte_row<BPP, SX, NW>(w, s, coff, xorv, std::make_integer_sequence<int, 8>{});
 }
@@ -567,14 +567,16 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     constexpr int MCUS = 32 / HS;               // MCUs per warp tile
     // tasks of one warp tile: luma rows, [K rows], then chroma
     constexpr int N_FULL = Fmt<CT>::NFULL * VS;
-    constexpr bool PAIRED = SUB && HS == 2; // two 1x1 components share a task (16 blocks each) when chroma is horizontally decimated
-    constexpr int N_CHROMA = PAIRED ? (Fmt<CT>::NSUB + 1) / 2 : Fmt<CT>::NSUB;
+    // when chroma is horizontally decimated a 1x1 component has only 32 / HS blocks per tile: HS of them share a task
+    constexpr bool PAIRED = SUB && HS >= 2;
+    constexpr int LPC = 32 / HS; // lanes (blocks) per component in a shared task
+    constexpr int N_CHROMA = PAIRED ? (Fmt<CT>::NSUB + HS - 1) / HS : Fmt<CT>::NSUB;
     constexpr int N_TASKS_ROW = N_FULL + N_CHROMA;
     constexpr int N_TASKS = N_TASKS_ROW * MR;
 
     const int lane = threadIdx.x & 31;
     ChromaConsts cc{};
-    if constexpr (PAIRED && !BYTES && NCOMP > 1) cc = chroma_consts<CT>(lane >= 16);
+    if constexpr (PAIRED && !BYTES && NCOMP > 1) cc = chroma_consts<CT>(((lane / LPC) & 1) != 0);
     const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
     uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
@@ -660,10 +662,10 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
                 comp = Fmt<CT>::full_comp(task >= VS ? 1 : 0);
                 bv = task >= VS ? task - VS : task;
             } else if (PAIRED) {
-                const int ci = 2 * (task - N_FULL) + (lane >> 4);
-                if (ci >= Fmt<CT>::NSUB) continue; // an odd number of 1x1 components: the last task runs half empty
+                const int ci = HS * (task - N_FULL) + lane / LPC;
+                if (ci >= Fmt<CT>::NSUB) continue; // fewer 1x1 components than the task has room for: those lanes rest
                 comp = Fmt<CT>::sub_comp(ci);
-                bxl = lane & 15;
+                bxl = lane % LPC;
                 full = false;
             } else {
                 comp = Fmt<CT>::sub_comp(task - N_FULL);
@@ -800,7 +802,11 @@ cudaError_t launch_fast_ct(const StageAParams &p, dim3 block, size_t smem, cudaS
     if (p.hmax == 1 && p.vmax == 1) return launch_fast<CT, 1, 1>(p, block, smem, stream);
     if (p.hmax == 2 && p.vmax == 1) return launch_fast<CT, 2, 1>(p, block, smem, stream);
     if (p.hmax == 1 && p.vmax == 2) return launch_fast<CT, 1, 2>(p, block, smem, stream);
-    return launch_fast<CT, 2, 2>(p, block, smem, stream);
+    if (p.hmax == 2 && p.vmax == 2) return launch_fast<CT, 2, 2>(p, block, smem, stream);
+    if (p.hmax == 4 && p.vmax == 1) return launch_fast<CT, 4, 1>(p, block, smem, stream);
+    if (p.hmax == 4 && p.vmax == 2) return launch_fast<CT, 4, 2>(p, block, smem, stream);
+    if (p.hmax == 1 && p.vmax == 4) return launch_fast<CT, 1, 4>(p, block, smem, stream);
+    return launch_fast<CT, 2, 4>(p, block, smem, stream);
 }
 
 } // namespace

@@ -86,7 +86,10 @@ def test_generic_and_fast_stage_a_kernels_agree(monkeypatch):
     for color, sampling in (("rgb", (2, 2)), ("bgr", (2, 1)), ("rgba", (1, 2)), ("bgra", (1, 1)), ("luma", (1, 1)),
                             ("cmyk_as_ycck", (2, 2)), ("cmyk_as_ycck", (1, 1)), ("ycbcr", (2, 2)), ("ycbcr", (1, 1)), ("ycbcr", (2, 1)),
                             ("ycbcr", (1, 2)), ("ycck", (2, 2)), ("ycck", (1, 1)), ("ycck", (2, 1)), ("cmyk", (2, 2)), ("cmyk", (1, 1)),
-                            ("cmyk", (2, 1)), ("cmyk", (1, 2))):
+                            ("cmyk", (2, 1)), ("cmyk", (1, 2)),
+                            # factors of 4 (sequential scans): four 1x1 components' worth of lanes share a chroma task
+                            ("rgb", (4, 1)), ("rgb", (4, 2)), ("rgb", (1, 4)), ("rgb", (2, 4)), ("bgra", (4, 2)), ("cmyk_as_ycck", (4, 1)),
+                            ("cmyk_as_ycck", (2, 4)), ("ycbcr", (4, 1)), ("ycbcr", (1, 4)), ("ycck", (4, 2)), ("cmyk", (4, 1)), ("cmyk", (2, 4))):
         cfg = dict(quality=83, sampling=sampling)
         img = _img(color, 333, 77, seed=11)
         want = oracle_encode(img, 333, 77, color, cfg)
