@@ -45,7 +45,7 @@ WORKLOADS = {
     "x_ycbcr": (1920, 1080, "ycbcr", dict(quality=90, sampling=(2, 2)), 256, "batch of 1920x1080 YCbCr (verbatim) q90 4:2:0 baseline frames"),
     "x_cmyk": (4096, 4096, "cmyk", dict(quality=90, sampling=(2, 2)), 16, "batch of 4096x4096 CMYK (inverted) q90, K at 2x2, baseline frames"),
     "x_ycck": (4096, 4096, "ycck", dict(quality=90, sampling=(1, 1)), 16, "batch of 4096x4096 YCCK (verbatim) q90 4:4:4 baseline frames"),
-    "x_rgb411": (1920, 1080, "rgb", dict(quality=90, sampling=(4, 1)), 256, "batch of 1920x1080 RGB q90 4:1:1 (factor 4: sequential scans, generic colour+DCT kernel)"),
+    "x_rgb411": (1920, 1080, "rgb", dict(quality=90, sampling=(4, 1)), 256, "batch of 1920x1080 RGB q90 4:1:1 (factor 4: sequential scans)"),
     "c4a": (8192, 8192, "luma", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
             "1 x 8192x8192 grayscale q95 custom tables (BASELINE config 4a)"),
     "c4b": (8192, 8192, "cmyk_as_ycck", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,

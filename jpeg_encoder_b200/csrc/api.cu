@@ -583,10 +583,10 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 // memory -- what `Encoder::encode(&[u8])` hands over -- is staged through two pinned buffers owned by the context:
 // while the copy engine drains one, the host fills the other, so the DMA never waits for a page-locked bounce
 // inside the driver and the copy stays asynchronous.
-constexpr size_t kStageBytes = 8u << 20;
-// One core copies ~10 GB/s into pinned memory, a fifth of what the link takes: large pieces are split over a few threads.
+constexpr size_t kStageBytes = 16u << 20;
+// One core copies ~10 GB/s into pinned memory, a fifth of what the link takes: pieces of 8 MB and more are split over a few threads.
 void parallel_copy(void *dst, const uint8_t *src, size_t n) {
-    constexpr size_t kMinPerThread = 1u << 20;
+    constexpr size_t kMinPerThread = 4u << 20; // starting a thread costs as much as copying ~1 MB: a 1080p frame is copied by the caller alone
     unsigned threads = (unsigned)std::min<size_t>(4, n / kMinPerThread);
     const unsigned hw = std::thread::hardware_concurrency();
     if (hw && threads > hw) threads = hw;
