@@ -15,12 +15,14 @@ namespace jpgb {
 namespace {
 
 constexpr int kSym = 257;      // 256 symbols + the reserved code point (src/encoder.rs:1092-1095)
+constexpr int kPerLane = 9;    // ceil(257 / 32): entry i of the packed symbol list belongs to lane i % 32
 constexpr unsigned kNone = 0xFFFFFFFFu;
 
 struct TableSmem {
     uint32_t freq[kSym + 31];
     uint16_t root[kSym + 31], sym[kSym + 31]; // K.1 runs on the symbols that occur, packed to the front
     uint8_t csz[kSym + 31];                   // code size of packed entry i
+    uint16_t parent[2 * (kSym + 31)];         // merge tree: leaves 0..n-1 (the packed entries), inner nodes from n; 0xFFFF = no parent
     uint8_t codesize[kSym + 31];              // ... and of symbol s
     uint8_t values[256];
     uint8_t len[16];      // BITS after Figure K.3
@@ -29,19 +31,6 @@ struct TableSmem {
     uint32_t counter[34];
     uint32_t first_code[17], first_pos[17];
 };
-
-// local minimum of a lane: the least non-zero frequency among its entries, ties to the largest index
-__device__ __forceinline__ void lane_min(const uint32_t *freq, int lane, unsigned n, unsigned skip, uint32_t &f, unsigned &idx) {
-    f = kNone;
-    idx = kNone;
-    for (unsigned i = lane; i < n; i += 32) {
-        const uint32_t v = freq[i];
-        if (i != skip && v != 0 && v <= f) {
-            f = v;
-            idx = i;
-        }
-    }
-}
 
 // One warp builds one table. `freq_in` = 257 counts (entry 256 is forced to 1). Writes the kernel-format words
 // ((code length + value size) << 27 | code << size) and the DHT segment; returns false if a code does not fit.
@@ -63,42 +52,69 @@ __device__ bool build_one(TableSmem &S, const uint32_t *freq_in, bool ac, int ta
         if (sym < kSym + 31) S.codesize[sym] = 0;
         n += __popc(have);
     }
-    for (int i = lane; i < kSym + 31; i += 32) S.csz[i] = 0;
+    for (int i = lane; i < 2 * (kSym + 31); i += 32) S.parent[i] = 0xFFFF;
     __syncwarp();
+    // every lane keeps the frequencies of its (at most nine) entries in registers: entry i belongs to lane i % 32
+    uint32_t f[kPerLane];
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) f[j] = (unsigned)(lane + 32 * j) < n ? S.freq[lane + 32 * j] : 0u;
+    // least non-zero frequency among the lane's entries, ties to the largest index; `skip` is left out
+    auto lane_least = [&](unsigned skip, uint32_t &fo, unsigned &io) {
+        fo = kNone;
+        io = kNone;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const unsigned i = lane + 32 * j;
+            if (f[j] != 0 && i != skip && f[j] <= fo) {
+                fo = f[j];
+                io = i;
+            }
+        }
+    };
     uint32_t lf;
     unsigned li;
-    lane_min(S.freq, lane, n, kNone, lf, li);
+    lane_least(kNone, lf, li);
     bool ok = true;
-    for (;;) { // Figure K.1
+    // Figure K.1. What the reference keeps as linked lists (`others`, every member's code size bumped at each merge) is
+    // kept here as the merge tree itself: entry i currently stands for tree node root[i]; a merge hangs the two nodes
+    // under a new one. A symbol's code size is the depth of its leaf, read off the parent links afterwards.
+    unsigned next_node = n;
+    for (;;) {
         const uint32_t m1 = __reduce_min_sync(0xffffffffu, lf);
         if (m1 == kNone) break;
         const unsigned v1 = __reduce_max_sync(0xffffffffu, lf == m1 ? li : 0u); // indices of equal frequency: the largest
         // v2: the same rule over everything but v1; only v1's lane has to look again
         uint32_t lf2 = lf;
         unsigned li2 = li;
-        if ((v1 & 31) == (unsigned)lane) lane_min(S.freq, lane, n, v1, lf2, li2);
+        if ((v1 & 31) == (unsigned)lane) lane_least(v1, lf2, li2);
         const uint32_t m2 = __reduce_min_sync(0xffffffffu, lf2);
         if (m2 == kNone) break;
         const unsigned v2 = __reduce_max_sync(0xffffffffu, lf2 == m2 ? li2 : 0u);
-        __syncwarp(); // every lane has finished reading the frequencies of this round
         if (lane == 0) {
-            S.freq[v1] = m1 + m2;
-            S.freq[v2] = 0;
+            S.parent[S.root[v1]] = (uint16_t)next_node;
+            S.parent[S.root[v2]] = (uint16_t)next_node;
+            S.root[v1] = (uint16_t)next_node; // v1 now stands for the merged tree
         }
-        // every member of both trees moves one level down; v2's tree joins v1's. A tree is named after the entry
-        // that holds its frequency, which is exactly how v1 and v2 were found.
-        for (unsigned i = lane; i < n; i += 32) {
-            const unsigned r = S.root[i];
-            if (r == v1 || r == v2) {
-                const unsigned c = S.csz[i] + 1u;
-                if (c > 32) ok = false; // the reference panics on its fixed arrays
-                S.csz[i] = (uint8_t)(c > 255 ? 255 : c);
-                S.root[i] = (uint16_t)v1;
+        ++next_node;
+        // the merged frequency lives on at v1, v2 leaves the game: their owners update their registers and look again
+        const bool own1 = (v1 & 31) == (unsigned)lane, own2 = (v2 & 31) == (unsigned)lane;
+        if (own1 || own2) {
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                if (own1 && (int)(v1 >> 5) == j) f[j] = m1 + m2;
+                if (own2 && (int)(v2 >> 5) == j) f[j] = 0;
             }
+            lane_least(kNone, lf, li);
         }
-        __syncwarp();
-        if ((v1 & 31) == (unsigned)lane || (v2 & 31) == (unsigned)lane) lane_min(S.freq, lane, n, kNone, lf, li);
     }
+    __syncwarp();
+    for (unsigned i = lane; i < n; i += 32) { // depth of leaf i
+        unsigned d = 0, node = i;
+        while (S.parent[node] != 0xFFFF && d < 40) node = S.parent[node], ++d;
+        if (d > 32) ok = false; // the reference panics on its fixed arrays
+        S.csz[i] = (uint8_t)d;
+    }
+    __syncwarp();
     for (unsigned i = lane; i < n; i += 32) S.codesize[S.sym[i]] = S.csz[i]; // back to symbol order
     __syncwarp();
     if (n < 2) return false; // nothing but the reserved code point: no code at all (the reference indexes out of bounds and panics)
