@@ -170,7 +170,8 @@ int jpgb_encode_strip_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb
  *     with NCCL) and gathers the edge_dc arrays in strip order (n_strips * 8 values);
  *  3. jpgb_merge_strip_histograms re-chains the first DC difference of every strip to the block in front
  *     of it (the reference's histogram never resets the DC predictor, Q17) -> hist_total;
- *  4. every strip: jpgb_encode_strip_device_optimized with hist_total. */
+ *  4. every strip: jpgb_encode_strip_device_optimized with hist_total. When it follows step 1 on the same context, strip and
+ *     pixel pointer (the pixels untouched in between), the coefficients of step 1 are reused: the colour+DCT kernel runs once. */
 #define JPGB_HIST_WORDS (2 * 2 * 257)
 int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const jpgb_strip *strip, const void *d_pixels,
                                 uint32_t hist[JPGB_HIST_WORDS], int16_t edge_dc[8]);

@@ -138,6 +138,12 @@ struct jpgb_encoder {
     bool have_timing = false;
     uint32_t launches = 0;
     uint32_t last_piece_scans = 0; // scans of the last strip encode (its piece offsets are in piece_off)
+    // whose coefficients `coef` holds (set by jpgb_strip_histogram_device, cleared by every other call that writes `coef`):
+    // the optimized strip encode that follows on the same strip and pixels does not run the colour+DCT kernel again
+    bool coef_tagged = false;
+    PlanSig coef_sig{};
+    const void *coef_pixels = nullptr;
+    uint64_t coef_stride = 0;
     // replay of the launch sequence behind stage A as a CUDA graph (same settings, batch size and buffers)
     bool graphs_ok = true;
     struct CachedGraph {
@@ -228,10 +234,10 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     plan.fill_stage_a(ap);
 
     const uint64_t n_blocks = plan.blocks_per_image * n;
-    const uint64_t n_visits = plan.visits_per_image * n;
     const uint64_t n_segs = (uint64_t)plan.segs_per_image * n;
 
     CK(enc->coef.reserve(n_blocks * 128), "alloc coefficients");
+    if (!coef_ready) enc->coef_tagged = false;
     // ---- stage A (unless the caller has already run it slice by slice behind the upload) ----
     if (!coef_ready) {
         StageTimer t(enc, 0);
@@ -655,6 +661,7 @@ int encode_host_pipelined(jpgb_encoder *enc, const Plan &plan, const uint8_t *co
         const uint32_t n_slices = (plan.mcu_rows + rows_per_slice - 1) / rows_per_slice;
         CK(enc->pixels.reserve(stride), "alloc pixels");
         CK(enc->coef.reserve(plan.blocks_per_image * 128), "alloc coefficients");
+        enc->coef_tagged = false;
         while (enc->ev_slice.size() < n_slices) {
             cudaEvent_t e;
             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "create event");
@@ -1033,7 +1040,13 @@ static int encode_strip(jpgb_encoder *enc, const jpgb_params *p, const jpgb_stri
     timing_begin(enc);
     std::vector<uint64_t> off, pieces;
     const size_t stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
-    const int rc2 = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), stride, 1, off, &pieces, hist_total);
+    bool reuse = false;
+    if (hist_total && enc->coef_tagged && enc->coef_pixels == d_pixels && enc->coef_stride == uint64_t(stride)) {
+        const PlanSig sig = plan_sig(plan);
+        reuse = std::memcmp(&sig, &enc->coef_sig, sizeof(sig)) == 0;
+    }
+    const int rc2 = encode_device(enc, plan, static_cast<const uint8_t *>(d_pixels), stride, 1, off, &pieces, hist_total, reuse);
+    enc->coef_tagged = false;
     if (rc2 != JPGB_OK) return rc2;
     timing_end(enc);
     std::memcpy(piece_offsets, pieces.data(), pieces.size() * 8);
@@ -1090,6 +1103,10 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     CK(cudaStreamSynchronize(st), "histogram sync");
     std::memcpy(hist, enc->h_hist.p, hist_bytes);
     std::memcpy(edge_dc, edge, 16);
+    enc->coef_sig = plan_sig(plan);
+    enc->coef_pixels = d_pixels;
+    enc->coef_stride = uint64_t(ap.image_stride);
+    enc->coef_tagged = true;
     return JPGB_OK;
 }
 

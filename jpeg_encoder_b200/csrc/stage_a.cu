@@ -268,9 +268,11 @@ enum Role { ROLE_Y = 0, ROLE_CB = 1, ROLE_CR = 2, ROLE_K = 3, ROLE_RAW = 4, ROLE
 struct ChromaConsts;
 
 template <int CT>
+__host__ __device__ constexpr bool is_bgr() { return CT == JPGB_BGR || CT == JPGB_BGRA; }
+
+template <int CT>
 struct Fmt {
     static constexpr int BPP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_RGB || CT == JPGB_BGR || CT == JPGB_YCBCR) ? 3 : 4);
-    static constexpr bool BGR = CT == JPGB_BGR || CT == JPGB_BGRA;
     // formats whose samples are pixel bytes taken verbatim (Ycbcr, Ycck) or inverted (Cmyk): image_buffer.rs:206-257, 288-313
     static constexpr bool BYTES = CT == JPGB_YCBCR || CT == JPGB_YCCK || CT == JPGB_CMYK;
     static constexpr int NCOMP = CT == JPGB_LUMA ? 1 : ((CT == JPGB_CMYK_AS_YCCK || CT == JPGB_YCCK || CT == JPGB_CMYK) ? 4 : 3);
@@ -293,15 +295,15 @@ __device__ __forceinline__ int sample_at(const uint32_t (&w)[NW]) {
         return (int)__byte_perm(~w[(O + 3) >> 2], 0, 0x4440 + ((O + 3) & 3));
     } else if constexpr (ROLE == ROLE_Y) {
         // Y = (19595 R + 38470 G + 7471 B + 0x7FFF) >> 16            image_buffer.rs:22,26
-        if constexpr (Fmt<CT>::BGR) return dot3<O, 7471, 38470, 19595, RND>(w) >> 16;
+        if constexpr (is_bgr<CT>()) return dot3<O, 7471, 38470, 19595, RND>(w) >> 16;
         else return dot3<O, 19595, 38470, 7471, RND>(w) >> 16;
     } else if constexpr (ROLE == ROLE_CB) {
         // Cb = (-11059 R - 21709 G + 32768 B + (128 << 16) + 0x7FFF) >> 16   :23,27
-        if constexpr (Fmt<CT>::BGR) return dot3<O, 32768, -21709, -11059, MID>(w) >> 16;
+        if constexpr (is_bgr<CT>()) return dot3<O, 32768, -21709, -11059, MID>(w) >> 16;
         else return dot3<O, -11059, -21709, 32768, MID>(w) >> 16;
     } else {
         // Cr = (32768 R - 27439 G - 5329 B + (128 << 16) + 0x7FFF) >> 16     :24,28
-        if constexpr (Fmt<CT>::BGR) return dot3<O, -5329, -27439, 32768, MID>(w) >> 16;
+        if constexpr (is_bgr<CT>()) return dot3<O, -5329, -27439, 32768, MID>(w) >> 16;
         else return dot3<O, 32768, -27439, -5329, MID>(w) >> 16;
     }
 }
@@ -324,7 +326,7 @@ template <int CT>
 __device__ __forceinline__ ChromaConsts chroma_consts(bool cr) {
     auto pk = [](int a, int b) { return ((uint32_t)a & 0xFFFFu) | (((uint32_t)b & 0xFFFFu) << 16); };
     ChromaConsts c;
-    if (!Fmt<CT>::BGR) { // memory order R, G, B
+    if (!is_bgr<CT>()) { // memory order R, G, B
         if (!cr) { c.sA = pk(-11059, -21709); c.sB = 0; c.uA = 0; c.uB = pk(32768, 0); }
         else { c.sA = pk(0, -27439); c.sB = pk(-5329, 0); c.uA = pk(32768, 0); c.uB = 0; }
     } else {             // memory order B, G, R
