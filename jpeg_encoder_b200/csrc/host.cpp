@@ -609,9 +609,9 @@ void Plan::fill_stage_a(StageAParams &a) const {
     }
     a.tasks_per_group = n;
     // Warp kernel: every packed ColorType with luma factors in {1,2}; a task is (component, v, run of 32 consecutive blocks).
-    const bool fast_ct = true; // every ColorType and every sampling factor has a warp-kernel instantiation; planar input does not
+    const bool fast_ct = true; // every ColorType, every sampling factor and planar input have a warp-kernel instantiation
     const char *fg = std::getenv("JPGB_FORCE_GENERIC_STAGE_A"); // test hook
-    a.use_fast = !planar && fast_ct && !force_generic_stage_a && !(fg && fg[0] == '1');
+    a.use_fast = fast_ct && !force_generic_stage_a && !(fg && fg[0] == '1');
     // CTA tile: `groups` x 32 MCUs wide, one MCU row high; aim for ~24 KB of pixels in shared memory
     a.planar = planar ? 1 : 0;
     a.plane_stride = (unsigned long long)p.width * p.height;

@@ -718,6 +718,125 @@ __global__ void __launch_bounds__(128, 4) stage_a_warp_kernel(const __grid_const
     }
 }
 
+// =================================================================================================
+// Planar input (the ImageBuffer path, encoder.rs:506-515: full-resolution planes of samples taken verbatim).
+// One launch per component: a plane is a one-byte-per-sample image whose blocks cover 8*SX x 8*SY samples
+// (SX, SY = the component's decimation, point sampling as everywhere). Same warp-autonomous scheme as above:
+// a warp tile is 32 blocks of the component x MR block rows; only the sampled rows are staged (cp.async).
+// =================================================================================================
+template <int SX>
+__device__ __forceinline__ void load_row_plane(const uint8_t *row, int *s) {
+    constexpr int NW = ((7 * SX + 1) + 3) / 4;
+    uint32_t w[NW];
+    if constexpr (SX == 1) {
+        const uint2 a = *reinterpret_cast<const uint2 *>(row);
+        w[0] = a.x;
+        w[1] = a.y;
+    } else {
+        const uint4 *r = reinterpret_cast<const uint4 *>(row);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            const uint4 a = r[i];
+            w[4 * i] = a.x;
+            w[4 * i + 1] = a.y;
+            w[4 * i + 2] = a.z;
+            w[4 * i + 3] = a.w;
+        }
+    }
+    sample_row<JPGB_LUMA, ROLE_RAW, SX, NW>(w, s, std::make_integer_sequence<int, 8>{});
+}
+
+template <int SX>
+__host__ __device__ constexpr int plane_tile_block_rows() { return SX == 1 ? 4 : (SX == 2 ? 2 : 1); } // 8 KB per warp tile
+
+template <int SX, int SY>
+__global__ void __launch_bounds__(128, 4) stage_a_plane_kernel(const __grid_constant__ StageAParams p, const int comp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int MR = plane_tile_block_rows<SX>();
+    constexpr int PITCH = 256 * SX, ROWS = 8 * MR, TILE_BYTES = PITCH * ROWS;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned n_warps_total = (gridDim.x * blockDim.x) >> 5;
+    uint8_t *tile = smem + (threadIdx.x >> 5) * TILE_BYTES;
+    const int H = p.comp_h[comp], V = p.comp_v[comp];
+    // block columns and block rows this launch produces (the interleaved layout also holds the MCU padding)
+    const int tw = p.mcu_order ? p.comp_pw[comp] : p.comp_tw[comp];
+    const int th = p.mcu_order ? p.mcu_rows * V : min(p.mcu_rows * V, p.comp_th[comp] - p.mcu_row0 * V);
+    if (th <= 0) return;
+    const unsigned tiles_per_row = ((unsigned)tw + 31) / 32, tile_rows = ((unsigned)th + MR - 1) / MR;
+    const unsigned n_tiles = tiles_per_row * tile_rows * p.n_images;
+    const uint8_t *plane = p.pixels + (size_t)comp * p.plane_stride;
+    const int needed_total = tw * 8 * SX; // bytes of a row the blocks read (beyond `width`: the last sample repeated, Q4)
+
+    for (unsigned t = warp_global; t < n_tiles; t += n_warps_total) {
+        const unsigned tx = t % tiles_per_row, r = t / tiles_per_row;
+        const int by0 = (int)(r % tile_rows) * MR, img = (int)(r / tile_rows);
+        const int bx0 = (int)tx * 32;
+        const int px0 = bx0 * 8 * SX, py0 = by0 * 8 * SY;
+        const uint8_t *src = plane + (size_t)img * p.image_stride;
+        const int valid_px = min(PITCH, p.width - px0);
+        const int needed_bytes = min(PITCH, needed_total - px0);
+        __syncwarp(); // all lanes are done reading the previous tile
+        const bool interior = px0 + PITCH <= p.width && py0 + (ROWS - 1) * SY < p.height && (p.width & 15) == 0 &&
+                              ((reinterpret_cast<uintptr_t>(src) + (size_t)px0) & 15) == 0;
+        if (interior) {
+            const uint8_t *g = src + (size_t)py0 * p.width + px0 + lane * 16;
+            uint8_t *d = tile + lane * 16;
+#pragma unroll 4
+            for (int ry = 0; ry < ROWS; ++ry) {
+#pragma unroll
+                for (int c = 0; c < (PITCH + 511) / 512; ++c)
+                    if (c * 512 + 512 <= PITCH || lane * 16 + c * 512 < PITCH) cp_async16(d + c * 512, g + c * 512);
+                g += (size_t)SY * p.width;
+                d += PITCH;
+            }
+        } else {
+#pragma unroll 1
+            for (int ry = 0; ry < ROWS; ++ry) {
+                const int sy = min(py0 + ry * SY, p.height - 1);
+                const uint8_t *row = src + (size_t)sy * p.width + px0;
+                uint8_t *dst = tile + ry * PITCH;
+                const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+#pragma unroll 1
+                for (int cb = lane * 16; cb < needed_bytes; cb += 32 * 16) {
+                    if (aligned && cb + 16 <= valid_px) cp_async16(dst + cb, row + cb);
+                    else stage_edge_chunk<1>(dst, row, cb, valid_px);
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int mr = 0; mr < MR; ++mr) {
+            const int by = by0 + mr, bx = bx0 + lane;
+            if (by >= th) break;
+            if (bx >= tw) continue;
+            const uint8_t *base = tile + mr * 8 * PITCH + lane * 8 * SX;
+            int v[64];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) load_row_plane<SX>(base + y * PITCH, &v[y * 8]);
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+                dct8<1>(v[y * 8 + 0], v[y * 8 + 1], v[y * 8 + 2], v[y * 8 + 3], v[y * 8 + 4], v[y * 8 + 5], v[y * 8 + 6], v[y * 8 + 7]);
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+                dct8<2>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
+            const int gby = by + p.mcu_row0 * V; // block row inside the whole image
+            size_t blk = (size_t)img * p.blocks_per_image;
+            if (p.mcu_order) {
+                const int mcu_x = bx / H, bh = bx - mcu_x * H, gy = gby / V, bv = gby - gy * V;
+                blk += ((size_t)gy * p.mcu_cols + mcu_x) * p.bpu + p.slot_base[comp] + bv * H + bh;
+            } else {
+                blk += p.comp_off[comp] + (size_t)gby * p.comp_tw[comp] + bx;
+            }
+            int16_t *dst = p.coef + blk * 64;
+            if (p.comp_qt[comp] == 0) quantize_store256<0>(p, v, dst);
+            else quantize_store256<1>(p, v, dst);
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -811,6 +930,52 @@ cudaError_t launch_fast_ct(const StageAParams &p, dim3 block, size_t smem, cudaS
     return launch_fast<CT, 2, 4>(p, block, smem, stream);
 }
 
+template <int SX, int SY>
+cudaError_t launch_plane_variant(const StageAParams &p, int comp, cudaStream_t stream) {
+    constexpr int MR = plane_tile_block_rows<SX>();
+    const size_t smem = (size_t)4 * 256 * SX * 8 * MR;
+    auto kernel = stage_a_plane_kernel<SX, SY>;
+    static std::mutex mu;
+    static LaunchInfo cache[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    LaunchInfo info;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        LaunchInfo &c = cache[dev < kMaxDevices ? dev : kMaxDevices - 1];
+        if (!c.ready || c.dev != dev) {
+            cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev);
+            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.ctas_per_sm, kernel, 128, smem);
+            if (e != cudaSuccess) return e;
+            if (c.ctas_per_sm < 1) c.ctas_per_sm = 1;
+            c.dev = dev;
+            c.ready = true;
+        }
+        info = c;
+    }
+    const int tw = p.mcu_order ? p.comp_pw[comp] : p.comp_tw[comp], th = p.mcu_rows * p.comp_v[comp];
+    const unsigned long long n_tiles = (unsigned long long)((tw + 31) / 32) * ((th + MR - 1) / MR) * p.n_images;
+    unsigned long long grid = (unsigned long long)info.n_sms * info.ctas_per_sm;
+    if (grid * 4 > n_tiles) grid = (n_tiles + 3) / 4;
+    kernel<<<(unsigned)grid, 128, smem, stream>>>(p, comp);
+    return cudaGetLastError();
+}
+
+// planar input: one launch per component with the component's own decimation
+cudaError_t launch_planes(const StageAParams &p, cudaStream_t stream) {
+    for (int c = 0; c < p.ncomp; ++c) {
+        const int sx = p.hmax / p.comp_h[c], sy = p.vmax / p.comp_v[c];
+        cudaError_t e = cudaErrorInvalidValue;
+#define JPGB_PLANE(X, Y) \
+    if (sx == X && sy == Y) e = launch_plane_variant<X, Y>(p, c, stream);
+        JPGB_PLANE(1, 1) JPGB_PLANE(2, 1) JPGB_PLANE(1, 2) JPGB_PLANE(2, 2)
+        JPGB_PLANE(4, 1) JPGB_PLANE(4, 2) JPGB_PLANE(1, 4) JPGB_PLANE(2, 4) JPGB_PLANE(4, 4)
+#undef JPGB_PLANE
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 } // namespace
 
 cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStream_t stream) {
@@ -820,7 +985,8 @@ cudaError_t launch_stage_a(const StageAParams &p_in, uint32_t n_images, cudaStre
     const int n_tasks = p.groups * p.tasks_per_group;
     const int warps = n_tasks < 8 ? n_tasks : 8;
     dim3 grid(p.tiles_per_row, p.mcu_rows, 1), block(warps * 32);
-    if (p.use_fast && !p.planar) {
+    if (p.use_fast && p.planar) return launch_planes(p, stream);
+    if (p.use_fast) {
         switch (p.color_type) {
         case JPGB_LUMA: return launch_fast<JPGB_LUMA, 1, 1>(p, block, smem, stream);
         case JPGB_RGB: return launch_fast_ct<JPGB_RGB>(p, block, smem, stream);

@@ -10,7 +10,7 @@ fn main() {
     let mut cmd = Command::new(&nvcc);
     cmd.args(["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib);
-    for f in ["api.cu", "stage_a.cu", "entropy.cu", "tables.cu", "scan.cu", "host.cpp"] {
+    for f in ["api.cu", "stage_a.cu", "entropy.cu", "tables.cu", "gather.cu", "scan.cu", "host.cpp"] {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

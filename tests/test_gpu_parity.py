@@ -619,6 +619,25 @@ def test_encode_planes_all_jpeg_color_types(kind):
         assert got == oracle_encode(ref_in, w, h, kind, cfg)
 
 
+@pytest.mark.parametrize("sampling", [(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (4, 2), (1, 4), (2, 4)])
+def test_planar_warp_kernel_against_generic_kernel_and_oracle(sampling, monkeypatch):
+    """Planar input has its own warp kernel (one launch per plane, the plane's decimation as template arguments):
+    interior tiles (cp.async of whole rows), right / bottom edges (replication, Q4), unaligned widths, every sampling."""
+    import jpeg_encoder_b200 as je
+    for kind, (w, h) in (("ycbcr", (1040, 100)), ("ycck", (531, 70)), ("cmyk", (1296, 41)), ("luma", (1029, 67))):
+        jct = {"luma": je.JpegColorType.Luma, "ycbcr": je.JpegColorType.Ycbcr, "cmyk": je.JpegColorType.Cmyk, "ycck": je.JpegColorType.Ycck}[kind]
+        n = jct.get_num_components()
+        planes = [images.photo_like(w, h, 1, seed=70 + c) for c in range(n)]
+        packed = planes[0] if n == 1 else np.stack(planes, -1)
+        ref_in = 255 - packed if kind == "cmyk" else packed
+        for cfg in (dict(quality=85, sampling=sampling), dict(quality=85, sampling=sampling, restart_interval=9, optimize_huffman=True)):
+            want = oracle_encode(ref_in, w, h, kind, cfg)
+            assert make_encoder(cfg).encode_planes(planes, w, h, jct) == want, (kind, cfg)
+            monkeypatch.setenv("JPGB_FORCE_GENERIC_STAGE_A", "1")
+            assert make_encoder(cfg).encode_planes(planes, w, h, jct) == want, (kind, cfg, "generic")
+            monkeypatch.delenv("JPGB_FORCE_GENERIC_STAGE_A")
+
+
 def test_concurrent_contexts_on_threads():
     """One jpgb_encoder context per host thread (the reference's Encoder is Send, not shared): four threads
     encode different configurations at the same time on their own streams; every result must stay exact."""

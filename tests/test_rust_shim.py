@@ -124,3 +124,15 @@ def test_params_struct_field_order(shim):
     r_body = re.search(r"struct JpgbParams \{(.*?)\}", shim).group(1)
     r_fields = re.findall(r"(\w+):", r_body)
     assert r_fields == c_fields
+
+
+def test_build_script_compiles_every_source():
+    """rust/build.rs names each translation unit of csrc/ (a missing one is an unresolved symbol at cargo build time)"""
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "rust", "build.rs")).read()
+    src = glob.glob(os.path.join(root, "jpeg_encoder_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "jpeg_encoder_b200", "csrc", "*.cpp"))
+    assert src
+    for s in src:
+        assert '"%s"' % os.path.basename(s) in text, os.path.basename(s)
