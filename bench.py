@@ -285,6 +285,8 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rank_ms = []
+
     def timed_device(n_frames, stage_timers=False):
         """K timed steps of the device-resident path over the first n_frames resident frames: (ms per step max over
         ranks, per-stage ms, launches). With stage_timers the library brackets every stage with CUDA events (and
@@ -306,8 +308,10 @@ def run_product(args):
         ms_ = e0.elapsed_time(e1)
         if world > 1:
             t_ = torch.tensor([ms_], device=dev_t)
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            ms_ = float(t_.item())
+            all_ = [torch.zeros_like(t_) for _ in range(world)]
+            dist.all_gather(all_, t_)
+            rank_ms[:] = [float(x.item()) / args.steps for x in all_]  # every rank's own time: shows a straggler
+            ms_ = max(float(x.item()) for x in all_)
         return ms_ / args.steps, stage_ms_, launches_
 
     # ---- device-resident timing ----
@@ -318,6 +322,7 @@ def run_product(args):
         sampler.start()
         time.sleep(0.3)
     ms_per_step, _, launches = timed_device(batch)
+    rank_ms_value = list(rank_ms)
     _, stage_ms, _ = timed_device(batch, stage_timers=True)  # second pass: per-stage breakdown and the roofline numerator
     device.set_timing(False)
     if rank == 0:
@@ -507,6 +512,8 @@ def run_product(args):
     }
     if weak:
         line["weak"] = weak
+    if rank_ms_value:
+        line["rank_ms_per_step"] = [round(x, 4) for x in rank_ms_value]
     if c5:
         line["c5"] = c5
     print(json.dumps(line))

@@ -119,8 +119,8 @@ struct jpgb_encoder {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    DevBuf pixels, coef, huff, hdr, hdr_len, scratch, pool, chunk_bits, chunk_pool, chunk_bitpos, seglen, segpos, ustream, raw_mask, ffcount, ffpos,
-        out, file_off, scan_tmp, hist, piece_off, out2, pixels2, status, aux_status, hdr_parts, scan_err;
+    DevBuf pixels, coef, huff, hdr, hdr_len, scratch, pool, chunk_bits, chunk_pool, chunk_bitpos, seglen, segpos, ustream, ffcount, ffpos,
+        out, scan_tmp, hist, piece_off, out2, pixels2, status, aux_status, hdr_parts;
     std::vector<uint8_t> last_tables; // what the device currently holds
     double ucap_ratio = 0; // unstuffed-stream bytes to provision per raw pixel byte, learnt from earlier calls
     double pool_ratio = 0; // the same for the chunk pool (code bytes incl. per-chunk alignment)
@@ -248,9 +248,10 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         enc->launches += 1;
     }
 
-    CK(enc->status.reserve(kStatusWords * 8), "alloc status");
-    CK(enc->aux_status.reserve(kStatusWords * 8), "alloc status");
-    unsigned long long *aux_status = enc->aux_status.as<unsigned long long>();
+    // One device buffer (allocated below, next to the stream it describes): [n + 1 file offsets][8 status words of the
+    // entropy stage (word 3: look-back scan error)][8 status words of the table build][raw-byte mask of the stream].
+    // The first three parts are read back with one copy; the last three are cleared with one memset.
+    unsigned long long *aux_status = nullptr, *scan_err = nullptr;
 
     // ---- Huffman tables and the file header (SOI/APPn prefix, SOF/DQT/DHT/DRI, first SOS -- Q21) ----
     // Default tables (Annex K.3): built on the host once per settings, shared by all images.
@@ -340,7 +341,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
             CK(launch_histogram(hp, enc->coef.as<int16_t>(), n, enc->hist.as<uint32_t>(), st), "histogram launch");
             enc->launches += 1;
         }
-        CK(cudaMemsetAsync(aux_status, 0, kStatusWords * 8, st), "clear table status");
         CK(launch_build_tables(enc->hist.as<uint32_t>(), 1, opt_tables, n, enc->huff.as<uint32_t>(), enc->hdr_parts.as<uint8_t>(), opt_head_len,
                                enc->hdr_parts.as<uint8_t>() + opt_head_len, opt_tail_len, enc->hdr.as<uint8_t>(), (uint32_t)hdr_stride,
                                enc->hdr_len.as<uint32_t>(), aux_status, st),
@@ -377,8 +377,6 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     b.hdr = enc->hdr.as<uint8_t>();
     b.hdr_stride = (uint32_t)hdr_stride;
 
-    CK(enc->scan_err.reserve(8), "alloc scan flag");
-    unsigned long long *scan_err = enc->scan_err.as<unsigned long long>();
 
     const uint64_t raw_bytes = (uint64_t)plan.p.width * plan.p.height * plan.bpp * n;
     // learnt bytes per raw byte from earlier calls on this context, else a third of the raw size
@@ -388,10 +386,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
     // every chunk is rounded up to 16 bytes in the pool
     uint64_t pool_units = (enc->pool_ratio > 0 ? (uint64_t)(raw_bytes * enc->pool_ratio) : raw_bytes / 3) / 16 + n_chunks + 4096;
     uint64_t ubytes = 0, total = 0, pool_used = 0;
-    CK(enc->file_off.reserve((size_t)(n + 1) * 8), "alloc file offsets");
-    CK(enc->h_small.reserve(128 + (size_t)(n + 1) * 8), "alloc readback");
-    b.file_off = enc->file_off.as<unsigned long long>();
-    b.status = enc->status.as<unsigned long long>();
+    CK(enc->h_small.reserve((size_t)(2 * kStatusWords + n + 1) * 8), "alloc readback");
     b.n_segs_total = n_segs;
     // Capacities are sticky per (settings, batch size): steady-state calls provision exactly what the last successful
     // call used, so the launch sequence below has identical parameters call after call and is replayed as a CUDA graph.
@@ -410,7 +405,8 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         ucap = (ucap + kStuffChunk - 1) / kStuffChunk * kStuffChunk;
         const uint64_t n_pieces = ucap / kStuffChunk;
         CK(enc->ustream.reserve(ucap + 64), "alloc unstuffed stream");
-        CK(enc->raw_mask.reserve((ucap / 32 + 2) * 4), "alloc raw mask");
+        const size_t mask_bytes = (size_t)(ucap / 32 + 2) * 4;
+        CK(enc->status.reserve((size_t)(n + 1 + 2 * kStatusWords) * 8 + mask_bytes), "alloc status and raw mask");
         CK(enc->ffcount.reserve((n_pieces + 1) * 4), "alloc ff counts");
         CK(enc->ffpos.reserve((n_pieces + 2) * 8), "alloc ff positions");
         CK(enc->scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(n_pieces, std::max(n_chunks, n_segs)))), "alloc scan scratch");
@@ -424,7 +420,11 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         b.pool = enc->pool.as<uint32_t>();
         b.pool_cap = pool_units;
         b.ustream = enc->ustream.as<uint8_t>();
-        b.raw_mask = enc->raw_mask.as<uint32_t>();
+        b.file_off = enc->status.as<unsigned long long>();
+        b.status = b.file_off + (n + 1);
+        aux_status = b.status + kStatusWords;
+        scan_err = b.status + 3;
+        b.raw_mask = reinterpret_cast<uint32_t *>(b.status + 2 * kStatusWords);
         b.ffcount = enc->ffcount.as<uint32_t>();
         b.ffpos = enc->ffpos.as<unsigned long long>();
         b.scan_tmp = enc->scan_tmp.p;
@@ -433,46 +433,49 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         b.out_cap = ocap;
         const bool with_tables = optimized && attempt == 0, with_coder = !coded;
         auto enqueue = [&]() -> int {
+            // status words of the coder (all, or all but the pool cursor when only the tail is repeated) and of the table build
+            if (with_coder) {
+                CK(cudaMemsetAsync(b.status, 0, 2 * kStatusWords * 8 + mask_bytes, st), "clear status and raw mask");
+            } else { // the pool cursor (and the table status) stay
+                CK(cudaMemsetAsync(b.status, 0, 4 * 8, st), "clear status");
+                CK(cudaMemsetAsync(b.raw_mask, 0, mask_bytes, st), "clear raw mask");
+            }
             if (with_tables) {
                 const int rc = enqueue_tables();
                 if (rc != JPGB_OK) return rc;
             }
             if (with_coder) {
                 StageTimer t(enc, 2);
-                CK(cudaMemsetAsync(b.status, 0, kStatusWords * 8, st), "clear status");
-                CK(cudaMemsetAsync(scan_err, 0, 8, st), "clear scan flag");
                 CK(launch_encode_chunks(b, hp, n, coder, st), "coding launch");
-                CK(launch_exclusive_scan(b.chunk_bits, b.chunk_bitpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "chunk position scan");
-                CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
-                CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches, scan_err), "segment position scan");
-                enc->launches += 2;
-            } else {
-                CK(cudaMemsetAsync(b.status, 0, 4 * 8, st), "clear status"); // keeps the pool cursor
+                enc->launches += 1;
+                const bool few_chunks = n_chunks <= 4096, few_segs = n_segs <= 4096;
+                if (!few_chunks) CK(launch_exclusive_scan(b.chunk_bits, b.chunk_bitpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "chunk position scan");
+                if (few_segs) { // chunk positions (when few), segment lengths and positions in one single-CTA launch
+                    CK(launch_positions(b, hp, n, few_chunks, st), "positions launch");
+                    enc->launches += 1;
+                } else {
+                    if (few_chunks) CK(launch_exclusive_scan(b.chunk_bits, b.chunk_bitpos, n_chunks, b.scan_tmp, st, &enc->launches, scan_err), "chunk position scan");
+                    CK(launch_segment_lengths(b, hp, n, st), "segment length launch");
+                    CK(launch_exclusive_scan(b.seglen, b.segpos, n_segs, b.scan_tmp, st, &enc->launches, scan_err), "segment position scan");
+                    enc->launches += 1;
+                }
             }
             {
                 StageTimer t(enc, 3);
-                CK(launch_zero_ustream(b, n_segs, st), "zero stream launch");
                 CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
                 CK(launch_place_chunks(b, hp, n, st), "placement launch");
-                enc->launches += 3;
+                enc->launches += 2;
             }
             {
                 StageTimer t(enc, 4);
                 CK(launch_count_ff(b, st), "count ff launch");
-                CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_pieces, b.scan_tmp, st, &enc->launches, scan_err), "ff scan");
-                CK(launch_stuff_scatter(b, st), "scatter launch");
-                CK(launch_file_offsets(b, hp, n, st), "file offsets launch");
-                enc->launches += 3;
-                if (piece_offsets) { // strip mode: where each scan's bytes start
-                    const size_t np = plan.scans.size() + 1;
-                    CK(launch_scan_offsets(b, hp, enc->piece_off.as<unsigned long long>(), st), "scan offsets launch");
-                    enc->launches += 1;
-                    CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, np * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
-                }
-                CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + 128, b.file_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "read file offsets");
-                CK(cudaMemcpyAsync(enc->h_small.p, b.status, kStatusWords * 8, cudaMemcpyDeviceToHost, st), "read status");
-                CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + kStatusWords * 8, scan_err, 8, cudaMemcpyDeviceToHost, st), "read scan flag");
-                if (optimized) CK(cudaMemcpyAsync(enc->h_small.as<uint8_t>() + kStatusWords * 8 + 8, aux_status + 2, 8, cudaMemcpyDeviceToHost, st), "read table flag");
+                if (ff_scan_needed(b)) CK(launch_exclusive_scan(b.ffcount, b.ffpos, n_pieces, b.scan_tmp, st, &enc->launches, scan_err), "ff scan");
+                // ... and the file offsets (for a strip also where each scan's bytes start) by extra CTAs of the same launch
+                CK(launch_stuff_scatter(b, hp, n, piece_offsets ? enc->piece_off.as<unsigned long long>() : nullptr, st), "scatter launch");
+                enc->launches += 2;
+                if (piece_offsets)
+                    CK(cudaMemcpyAsync(enc->h_pieces.p, enc->piece_off.p, (plan.scans.size() + 1) * 8, cudaMemcpyDeviceToHost, st), "read piece offsets");
+                CK(cudaMemcpyAsync(enc->h_small.p, b.file_off, (size_t)(n + 1 + 2 * kStatusWords) * 8, cudaMemcpyDeviceToHost, st), "read file offsets and status");
             }
             return JPGB_OK;
         };
@@ -535,10 +538,10 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
             if (rc != JPGB_OK) return rc;
         }
         CK(cudaStreamSynchronize(st), "final sync");
-        const uint64_t *status = enc->h_small.as<uint64_t>();
-        if (status[kStatusWords] || status[3]) return fail(enc, JPGB_ERR_CUDA, "internal: prefix-sum look-back timed out");
+        const uint64_t *status = enc->h_small.as<uint64_t>() + (n + 1);
+        if (status[3]) return fail(enc, JPGB_ERR_CUDA, "internal: prefix-sum look-back timed out");
         if (status[2] & 8) return fail(enc, JPGB_ERR_BAD_PARAMS, "a scan segment exceeds 4 GiB (use a restart interval)");
-        if (optimized && (status[kStatusWords + 1] & 16)) return fail(enc, JPGB_ERR_HUFFMAN, "an optimized Huffman code does not fit (longer than 32 bits, or code plus value bits beyond 31)");
+        if (optimized && (status[kStatusWords + 2] & 16)) return fail(enc, JPGB_ERR_HUFFMAN, "an optimized Huffman code does not fit (longer than 32 bits, or code plus value bits beyond 31)");
         ubytes = status[0];
         pool_used = status[5];
         if (status[2] == 0) {
@@ -579,7 +582,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         piece_offsets->assign(enc->h_pieces.as<uint64_t>(), enc->h_pieces.as<uint64_t>() + plan.scans.size() + 1);
         enc->last_piece_scans = (uint32_t)plan.scans.size();
     }
-    offsets.assign(enc->h_small.as<uint64_t>() + 16, enc->h_small.as<uint64_t>() + 16 + n + 1);
+    offsets.assign(enc->h_small.as<uint64_t>(), enc->h_small.as<uint64_t>() + n + 1);
     enc->out_total = total;
     if (offsets[n] != total) return fail(enc, JPGB_ERR_CUDA, "internal: file offsets disagree with stream size");
     return JPGB_OK;
@@ -841,7 +844,7 @@ void jpgb_encoder_destroy(jpgb_encoder *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pixels, &e->coef, &e->huff, &e->hdr, &e->hdr_len, &e->scratch, &e->pool, &e->chunk_bits, &e->chunk_pool, &e->chunk_bitpos, &e->seglen, &e->segpos,
-                      &e->ustream, &e->raw_mask, &e->ffcount, &e->ffpos, &e->out, &e->file_off, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status, &e->aux_status, &e->hdr_parts, &e->scan_err};
+                      &e->ustream, &e->ffcount, &e->ffpos, &e->out, &e->scan_tmp, &e->hist, &e->piece_off, &e->out2, &e->pixels2, &e->status, &e->aux_status, &e->hdr_parts};
     for (DevBuf *b : bufs) b->release();
     e->h_small.release();
     e->h_hist.release();

@@ -528,35 +528,104 @@ __global__ void __launch_bounds__(256) segment_len_kernel(const __grid_constant_
     b.seglen[g] = (unsigned)bytes;
 }
 
+// bytes of local segment g (lead + data + EOI); raises flag 8 beyond 4 GiB
+__device__ __forceinline__ unsigned long long segment_bytes(const EntropyBuffers &b, const DevPlan &P, unsigned long long g) {
+    const unsigned long long img = g / P.segs_per_image;
+    const unsigned s = (unsigned)(g - img * P.segs_per_image);
+    const int k = find_scan_by_seg(P, s);
+    const DevScan &S = P.scans[k];
+    const unsigned i = s - S.seg_base;
+    const unsigned cps = P.groups[k % P.n_groups].cps;
+    const unsigned long long c0 = img * P.chunks_per_image + S.chunk_base + (unsigned long long)i * cps;
+    const unsigned long long bits = b.chunk_bitpos[c0 + cps] - b.chunk_bitpos[c0];
+    const unsigned tail = (s == P.segs_per_image - 1 && P.has_eoi) ? 2u : 0u;
+    return lead_len(b, P, img, k, i) + ((bits + 7) >> 3) + tail;
+}
+
+// exclusive prefix over the 1024 threads of a CTA (sm: 33 words); `total` = the CTA's sum
+__device__ __forceinline__ unsigned long long cta1024_exclusive(unsigned long long v, unsigned long long *sm, unsigned long long &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = sm[lane];
+        unsigned long long winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += o;
+        }
+        sm[lane] = winc - w;
+        if (lane == 31) sm[32] = winc;
+    }
+    __syncthreads();
+    const unsigned long long ex = sm[warp] + inc - v;
+    total = sm[32];
+    __syncthreads(); // sm is reused by the caller's next round
+    return ex;
+}
+
+// Small jobs (a few thousand chunks and segments: one image, or a short batch): the prefix sum of the chunk sizes, the
+// segment lengths and their prefix sum in ONE single-CTA kernel instead of four launches. With scan_chunks == 0 the
+// chunk positions come from the look-back scan (many chunks, few segments).
+__global__ void __launch_bounds__(1024) positions_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_chunks,
+                                                         unsigned long long n_segs, int scan_chunks) {
+    __shared__ unsigned long long sm[33];
+    unsigned long long carry = 0, total;
+    if (scan_chunks) {
+        for (unsigned long long base = 0; base < n_chunks; base += 1024) {
+            const unsigned long long i = base + threadIdx.x;
+            const unsigned long long ex = cta1024_exclusive(i < n_chunks ? b.chunk_bits[i] : 0ull, sm, total);
+            if (i < n_chunks) b.chunk_bitpos[i] = carry + ex;
+            carry += total;
+        }
+        if (threadIdx.x == 0) b.chunk_bitpos[n_chunks] = carry;
+        __syncthreads(); // the positions are read back below by other threads of this CTA
+    }
+    carry = 0;
+    for (unsigned long long base = 0; base < n_segs; base += 1024) {
+        const unsigned long long g = base + threadIdx.x;
+        unsigned long long bytes = 0;
+        if (g < n_segs) {
+            bytes = segment_bytes(b, P, g);
+            if (bytes > 0xFFFFFFFFull) atomicOr(b.status + 2, 8ull);
+        }
+        const unsigned long long ex = cta1024_exclusive(bytes, sm, total);
+        if (g < n_segs) b.segpos[g] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) b.segpos[n_segs] = carry;
+}
+
 // Unstuffed stream size as computed on the device; kernels that write the stream bail out (and the
 // first one raises the overflow flag) when it exceeds the capacity the host provided.
 __device__ __forceinline__ unsigned long long stream_bytes(const EntropyBuffers &b) { return b.segpos[b.n_segs_total]; }
 __device__ __forceinline__ bool stream_fits(const EntropyBuffers &b) { return stream_bytes(b) <= b.ustream_cap; }
-
-__global__ void __launch_bounds__(256) zero_ustream_kernel(const EntropyBuffers b, unsigned long long n_segs_total) {
-    const unsigned long long bytes = b.segpos[n_segs_total];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        b.status[0] = bytes;
-        if (bytes > b.ustream_cap) atomicOr(b.status + 2, 1ull);
-    }
-    if (bytes > b.ustream_cap) return;
-    const unsigned long long n16 = (bytes + 15) >> 4, nm = ((bytes + 31) >> 5);
-    uint4 *u = reinterpret_cast<uint4 *>(b.ustream);
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
-        u[i] = make_uint4(0, 0, 0, 0);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += stride) b.raw_mask[i] = 0;
-}
 
 __device__ __forceinline__ void put_raw(const EntropyBuffers &b, unsigned long long pos, uint8_t byte) {
     b.ustream[pos] = byte;
     atomicOr(b.raw_mask + (pos >> 5), 1u << (pos & 31));
 }
 
-__global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_segs) {
-    // one warp per segment; lanes stride over the lead bytes (headers can be long: ICC, EXIF)
-    const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long n_segs,
+                                                           const unsigned wps) {
+    // `wps` warps per segment: each takes a slice of the segment's chunk boundaries; the first one also writes the lead
+    // (lanes stride over its bytes: headers can be long -- ICC, EXIF) and the EOI
+    const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long g = gw / wps;
+    const unsigned slice = (unsigned)(gw - g * wps);
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // size of the unstuffed stream for the host; too large for the buffer: nothing is written
+        const unsigned long long bytes = stream_bytes(b);
+        b.status[0] = bytes;
+        if (bytes > b.ustream_cap) atomicOr(b.status + 2, 1ull);
+    }
     if (g >= n_segs || !stream_fits(b)) return;
     const unsigned long long img = g / P.segs_per_image;
     const unsigned s = (unsigned)(g - img * P.segs_per_image);
@@ -564,6 +633,29 @@ __global__ void __launch_bounds__(128) segment_lead_kernel(const __grid_constant
     const DevScan &S = P.scans[k];
     const unsigned i = s - S.seg_base;
     const unsigned long long pos = b.segpos[g];
+    {   // The stream is not cleared as a whole. The placement kernel stores the words a chunk owns and ORs its bits into
+        // the words it shares: the word in which a chunk ends and the next one begins (every chunk boundary that is not
+        // word aligned, the segment's first and last data bit included). Those words are zeroed here -- only their bytes
+        // that hold this segment's entropy-coded data: lead, EOI and the neighbouring segments' bytes in the same word
+        // are stored byte-wise by whoever owns them, in any order.
+        const bool eoi = s == P.segs_per_image - 1 && P.has_eoi;
+        const unsigned cps = P.groups[k % P.n_groups].cps;
+        const unsigned long long c0 = img * P.chunks_per_image + S.chunk_base + (unsigned long long)i * cps;
+        const unsigned long long bit0 = b.chunk_bitpos[c0];
+        const unsigned long long data0 = pos + lead_len(b, P, img, k, i), data1 = b.segpos[g + 1] - (eoi ? 2u : 0u);
+        const unsigned per = (cps + wps) / wps; // cps + 1 boundaries over wps warps
+        const unsigned q1 = (slice + 1) * per < cps + 1 ? (slice + 1) * per : cps + 1;
+        for (unsigned q = slice * per + lane; q < q1; q += 32) {
+            const unsigned long long pbit = data0 * 8 + (b.chunk_bitpos[c0 + q] - bit0);
+            if ((pbit & 31) == 0) continue;
+            const unsigned long long w = pbit >> 5;
+            const unsigned long long lo = w * 4 > data0 ? w * 4 : data0, hi = w * 4 + 4 < data1 ? w * 4 + 4 : data1;
+            if (lo + 4 == hi) reinterpret_cast<uint32_t *>(b.ustream)[w] = 0u;
+            else
+                for (unsigned long long x = lo; x < hi; ++x) b.ustream[x] = 0;
+        }
+    }
+    if (slice != 0) return;
     if (S.rst_base + i > 0) {
         if (lane == 0) {
             put_raw(b, pos, 0xFF);
@@ -720,24 +812,92 @@ __global__ void __launch_bounds__(256) count_ff_kernel(const EntropyBuffers b) {
     }
 }
 
-__global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers b, unsigned long long n_chunks_cap) {
+// Short streams (up to kDirectPieces pieces): no prefix-sum launch over the per-piece 0xFF counts; whoever needs
+// "0xFF bytes in front of piece i" adds the counts up itself.
+constexpr unsigned kDirectPieces = 2048;
+
+// sum of ffcount[0, idx) and of all n_pieces counts, by one warp
+__device__ __forceinline__ void ff_sums_warp(const uint32_t *ffcount, unsigned n_pieces, unsigned idx, int lane, unsigned long long &before, unsigned long long &total) {
+    unsigned a = 0, t = 0;
+    for (unsigned j = lane; j < n_pieces; j += 32) {
+        const unsigned v = ffcount[j];
+        t += v;
+        if (j < idx) a += v;
+    }
+    before = __reduce_add_sync(0xffffffffu, a);
+    total = __reduce_add_sync(0xffffffffu, t);
+}
+
+// data 0xFF bytes in [chunk start, pos) of the unstuffed stream, counted by one warp with 128-bit loads
+__device__ __forceinline__ unsigned ff_before_in_chunk(const EntropyBuffers &b, unsigned long long pos, int lane) {
+    const unsigned long long start = pos / kStuffChunk * kStuffChunk;
+    unsigned ff = 0;
+    for (unsigned long long i = start + (unsigned long long)lane * 16; i < pos; i += 32 * 16) {
+        const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + i);
+        const unsigned raw = (b.raw_mask[i >> 5] >> (i & 31)) & 0xFFFFu;
+        const unsigned valid = pos - i < 16 ? (unsigned)(pos - i) : 16u;
+        ff += ff_count16(d, raw, valid);
+    }
+    return __reduce_add_sync(0xffffffffu, ff);
+}
+
+// CTAs [0, n_pieces): piece blockIdx.x of the unstuffed stream -> its place in `out`, 0x00 inserted behind data 0xFF.
+// CTAs behind them, one warp per position: the byte offset in `out` of every file (position of the image's first
+// segment plus the data 0xFF bytes in front of it) and, for a strip, of every scan's first segment (the pieces).
+__global__ void __launch_bounds__(256) stuff_scatter_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned n_pieces,
+                                                            unsigned n_images, unsigned long long *piece_offs) {
     if (!stream_fits(b)) return;
     const unsigned long long bytes = stream_bytes(b);
-    {
-        const unsigned long long ff_total = b.ffpos[n_chunks_cap];
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            b.status[1] = ff_total;
-            if (bytes + ff_total > b.out_cap) atomicOr(b.status + 2, 2ull);
+    const bool direct = n_pieces <= kDirectPieces;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x >= n_pieces) { // ---- offsets ----
+        const unsigned k = (blockIdx.x - n_pieces) * 8 + warp;
+        const unsigned n_pos = n_images + 1 + (piece_offs ? (unsigned)P.n_scans + 1 : 0u);
+        if (k >= n_pos) return;
+        unsigned long long pos;
+        unsigned long long *dst;
+        if (k <= n_images) {
+            pos = k == n_images ? bytes : b.segpos[(unsigned long long)k * P.segs_per_image];
+            dst = b.file_off + k;
+        } else {
+            const unsigned sc = k - (n_images + 1);
+            pos = sc == (unsigned)P.n_scans ? bytes : b.segpos[P.scans[sc].seg_base];
+            dst = piece_offs + sc;
         }
-        if (bytes + ff_total > b.out_cap) return;
+        const unsigned long long piece = pos / kStuffChunk;
+        unsigned long long before, total;
+        if (direct) ff_sums_warp(b.ffcount, n_pieces, (unsigned)piece, lane, before, total);
+        else before = b.ffpos[piece];
+        const unsigned ff = ff_before_in_chunk(b, pos, lane);
+        if (lane == 0) *dst = pos + before + ff;
+        return;
     }
+    __shared__ unsigned warp_excl[9];
+    __shared__ unsigned long long ff_sm[2];
+    __shared__ __align__(16) uint8_t stage[2 * kStuffChunk + 32];
+    unsigned long long ff_before, ff_total;
+    if (direct) { // every CTA adds up the counts in front of its piece (and all of them) itself
+        if (warp == 0) {
+            unsigned long long a, t;
+            ff_sums_warp(b.ffcount, n_pieces, blockIdx.x, lane, a, t);
+            if (lane == 0) ff_sm[0] = a, ff_sm[1] = t;
+        }
+        __syncthreads();
+        ff_before = ff_sm[0];
+        ff_total = ff_sm[1];
+    } else {
+        ff_before = b.ffpos[blockIdx.x];
+        ff_total = b.ffpos[n_pieces];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.status[1] = ff_total;
+        if (bytes + ff_total > b.out_cap) atomicOr(b.status + 2, 2ull);
+    }
+    if (bytes + ff_total > b.out_cap) return;
     if ((unsigned long long)blockIdx.x * kStuffChunk >= bytes) return;
     // The chunk's output is first laid out in shared memory at the same offset modulo 16 as its place
     // in `out`, then copied with aligned 128-bit stores (single bytes only at the two ends).
-    __shared__ unsigned warp_excl[9];
-    __shared__ __align__(16) uint8_t stage[2 * kStuffChunk + 32];
     const unsigned long long base = (unsigned long long)blockIdx.x * kStuffChunk + (unsigned long long)threadIdx.x * 16;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 d = make_uint4(0, 0, 0, 0);
     unsigned m = 0, valid = 0;
     if (base < bytes) {
@@ -761,7 +921,7 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
     }
     __syncthreads();
     const unsigned long long chunk_base = (unsigned long long)blockIdx.x * kStuffChunk;
-    const unsigned long long out0 = chunk_base + b.ffpos[blockIdx.x]; // first output byte of this chunk
+    const unsigned long long out0 = chunk_base + ff_before; // first output byte of this chunk
     const unsigned pad = (unsigned)(out0 & 15);
     const unsigned chunk_in = bytes - chunk_base < kStuffChunk ? (unsigned)(bytes - chunk_base) : (unsigned)kStuffChunk;
     const unsigned total = chunk_in + warp_excl[8];
@@ -788,47 +948,6 @@ __global__ void __launch_bounds__(256) stuff_scatter_kernel(const EntropyBuffers
     }
 }
 
-// data 0xFF bytes in [chunk start, pos) of the unstuffed stream, counted by one warp with 128-bit loads
-__device__ __forceinline__ unsigned ff_before_in_chunk(const EntropyBuffers &b, unsigned long long pos, int lane) {
-    const unsigned long long start = pos / kStuffChunk * kStuffChunk;
-    unsigned ff = 0;
-    for (unsigned long long i = start + (unsigned long long)lane * 16; i < pos; i += 32 * 16) {
-        const uint4 d = *reinterpret_cast<const uint4 *>(b.ustream + i);
-        const unsigned raw = (b.raw_mask[i >> 5] >> (i & 31)) & 0xFFFFu;
-        const unsigned valid = pos - i < 16 ? (unsigned)(pos - i) : 16u;
-        ff += ff_count16(d, raw, valid);
-    }
-    return __reduce_add_sync(0xffffffffu, ff);
-}
-
-// byte offset of every file in `out`: position of the image's first segment plus the data 0xFF
-// bytes that precede it
-__global__ void __launch_bounds__(128) file_offsets_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned n_images) {
-    if (!stream_fits(b)) return;
-    const unsigned long long bytes = stream_bytes(b);
-    // one warp per file boundary; lanes stride over the (< kStuffChunk) bytes between the chunk start and it
-    const unsigned img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (img > n_images) return;
-    const unsigned long long pos = img == n_images ? bytes : b.segpos[(unsigned long long)img * P.segs_per_image];
-    const unsigned long long chunk = pos / kStuffChunk;
-    const unsigned ff = ff_before_in_chunk(b, pos, lane);
-    if (lane == 0) b.file_off[img] = pos + b.ffpos[chunk] + ff;
-}
-
-// final byte offset of the first segment of every scan of image 0 (+ the end): the pieces of a strip
-__global__ void __launch_bounds__(128) scan_offsets_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P, unsigned long long *offs) {
-    if (!stream_fits(b)) return;
-    const unsigned long long bytes = stream_bytes(b);
-    const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (k > (unsigned)P.n_scans) return;
-    const unsigned long long pos = k == (unsigned)P.n_scans ? bytes : b.segpos[P.scans[k].seg_base];
-    const unsigned long long chunk = pos / kStuffChunk;
-    const unsigned ff = ff_before_in_chunk(b, pos, lane);
-    if (lane == 0) offs[k] = pos + b.ffpos[chunk] + ff;
-}
-
 // ---- optimized-table histogram (encoder.rs:1086-1200) --------------------------------------------
 // One CTA per 256 consecutive blocks of one image, staged like a coding chunk (the coefficient buffer holds every
 // component's true grid in raster order -- optimized tables always code non-interleaved -- so the blocks are one
@@ -836,6 +955,27 @@ __global__ void __launch_bounds__(128) scan_offsets_kernel(const __grid_constant
 // non-zero mask, band by band: AC run/size symbols (runs restart per band), ZRL through the marker trick of the coder,
 // EOB when a band ends in zeros; DC category of the chained difference with NO restart resets (Q17).
 // Bins: [image][table][dc|ac][257], collected per CTA in shared memory. One launch for the whole batch.
+template <int BASE>
+__device__ __forceinline__ void count_half(unsigned m, int &next, unsigned c_shared, unsigned *ha) {
+#pragma unroll 1
+    while (m) { // same walk as code_half: the highest set bit of the reversed mask is the next position in zig-zag order
+        int p;
+        asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(m));
+        unsigned bit;
+        asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(bit) : "r"(p));
+        m ^= bit;
+        const int k = BASE + 31 - p;
+        int v;
+        asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(c_shared + 2 * k));
+        const int run = k - next; // <= 15 thanks to the markers; a marker is a zero: size 0 -> symbol 0xF0
+        next = k + 1;
+        const int a = v < 0 ? -v : v;
+        int top;
+        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(a));
+        atomicAdd(ha + ((run << 4) | (top + 1)), 1u);
+    }
+}
+
 __global__ void __launch_bounds__(256) histogram_kernel(const __grid_constant__ DevPlan P, const int16_t *coef, unsigned n_images, uint32_t *hist,
                                                         int bands, int per_band) {
     __shared__ unsigned sh[2 * 2 * 257];
@@ -880,21 +1020,16 @@ __global__ void __launch_bounds__(256) histogram_kernel(const __grid_constant__ 
             const int diff = (int)(int16_t)(mine[0] - prev);
             atomicAdd(h + (32 - __clz(diff < 0 ? -diff : diff)), 1u);
             unsigned *ha = h + 257;
+            const unsigned c_shared = (unsigned)__cvta_generic_to_shared(mine);
             for (int b = 0; b < bands; ++b) { // band b covers [max(b * per, 1), (b + 1) * per), the last one to 63
                 const int first_ac = b == 0 ? 1 : b * per_band, se = b == bands - 1 ? 63 : (b + 1) * per_band - 1;
                 if (se < first_ac) continue; // the empty first band of 34..64 scans
                 unsigned long long m = m_all & (~0ull << first_ac) & (~0ull >> (63 - se));
                 m |= zrl_markers(m, first_ac);
                 int next = first_ac;
-                while (m) {
-                    const int k = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const int c = mine[k];
-                    const int run = k - next; // <= 15 thanks to the markers; a marker is a zero: size 0 -> symbol 0xF0
-                    next = k + 1;
-                    atomicAdd(ha + ((run << 4) | (32 - __clz(c < 0 ? -c : c))), 1u);
-                }
-                if (next <= se) atomicAdd(ha, 1u);
+                count_half<0>(__brev((unsigned)m), next, c_shared, ha);
+                count_half<32>(__brev((unsigned)(m >> 32)), next, c_shared, ha);
+                if (next <= se) atomicAdd(ha, 1u); // the band ends in zeros: EOB
             }
         }
         __syncthreads();
@@ -994,15 +1129,17 @@ cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hp, u
     segment_len_kernel<<<grid_for(ns, 256), 256, 0, s>>>(b, hp, ns);
     return cudaGetLastError();
 }
-cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t s) {
-    // sized by the provisioned capacity (the real size is only known on the device): 16 KB per CTA pass
-    const unsigned long long want = (b.ustream_cap + 16383) / 16384;
-    zero_ustream_kernel<<<(unsigned)(want < 4096 ? (want ? want : 1) : 4096), 256, 0, s>>>(b, n_segs_total);
+cudaError_t launch_positions(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, bool scan_chunks, cudaStream_t s) {
+    positions_kernel<<<1, 1024, 0, s>>>(b, hp, (unsigned long long)hp.chunks_per_image * n, (unsigned long long)hp.segs_per_image * n, scan_chunks ? 1 : 0);
     return cudaGetLastError();
 }
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
     const unsigned long long ns = (unsigned long long)hp.segs_per_image * n;
-    segment_lead_kernel<<<grid_for(ns * 32, 128), 128, 0, s>>>(b, hp, ns);
+    unsigned cps = 1;
+    for (int g = 0; g < hp.n_groups; ++g) cps = hp.groups[g].cps > cps ? hp.groups[g].cps : cps;
+    unsigned wps = (cps + 1 + 127) / 128; // a warp looks at up to 128 chunk boundaries (four dependent loads per lane)
+    wps = wps > 1024 ? 1024 : wps;
+    segment_lead_kernel<<<grid_for(ns * wps * 32, 128), 128, 0, s>>>(b, hp, ns, wps);
     return cudaGetLastError();
 }
 cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
@@ -1017,17 +1154,11 @@ cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t s) {
     count_ff_kernel<<<grid_for(b.ustream_cap, kStuffChunk), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
-cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t s) {
-    const unsigned long long n_chunks_cap = (b.ustream_cap + kStuffChunk - 1) / kStuffChunk;
-    stuff_scatter_kernel<<<grid_for(b.ustream_cap, kStuffChunk), 256, 0, s>>>(b, n_chunks_cap);
-    return cudaGetLastError();
-}
-cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hp, unsigned long long *offs, cudaStream_t s) {
-    scan_offsets_kernel<<<grid_for((hp.n_scans + 1ull) * 32, 128), 128, 0, s>>>(b, hp, offs);
-    return cudaGetLastError();
-}
-cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, cudaStream_t s) {
-    file_offsets_kernel<<<grid_for((n + 1ull) * 32, 128), 128, 0, s>>>(b, hp, n);
+bool ff_scan_needed(const EntropyBuffers &b) { return grid_for(b.ustream_cap, kStuffChunk) > kDirectPieces; }
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, const DevPlan &hp, uint32_t n, unsigned long long *piece_offs, cudaStream_t s) {
+    const unsigned n_pieces = grid_for(b.ustream_cap, kStuffChunk);
+    const unsigned n_pos = n + 1 + (piece_offs ? (unsigned)hp.n_scans + 1 : 0u);
+    stuff_scatter_kernel<<<n_pieces + (n_pos + 7) / 8, 256, 0, s>>>(b, hp, n_pieces, n, piece_offs);
     return cudaGetLastError();
 }
 

@@ -66,14 +66,15 @@ struct CoderLaunch {
 cudaError_t coder_launch_config(const DevPlan &hplan, uint32_t n_images, CoderLaunch &cfg);
 cudaError_t launch_encode_chunks(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, const CoderLaunch &cfg, cudaStream_t stream);
 cudaError_t launch_segment_lengths(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
-cudaError_t launch_zero_ustream(const EntropyBuffers &b, uint64_t n_segs_total, cudaStream_t stream);
+// small jobs: chunk positions (scan_chunks), segment lengths and segment positions in one single-CTA launch
+cudaError_t launch_positions(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, bool scan_chunks, cudaStream_t stream);
 cudaError_t launch_segment_leads(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_place_chunks(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
 cudaError_t launch_count_ff(const EntropyBuffers &b, cudaStream_t stream);   // grids sized by b.ustream_cap
-cudaError_t launch_stuff_scatter(const EntropyBuffers &b, cudaStream_t stream);
-cudaError_t launch_scan_offsets(const EntropyBuffers &b, const DevPlan &hplan, unsigned long long *offs,
-                                cudaStream_t stream);
-cudaError_t launch_file_offsets(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, cudaStream_t stream);
+// short streams: the scatter launch adds up the per-piece 0xFF counts itself and the prefix-sum launch is skipped
+bool ff_scan_needed(const EntropyBuffers &b);
+// pieces -> out, plus the file offsets (b.file_off) and, with piece_offs, the offset of every scan's first segment
+cudaError_t launch_stuff_scatter(const EntropyBuffers &b, const DevPlan &hplan, uint32_t n_images, unsigned long long *piece_offs, cudaStream_t stream);
 
 // tables.cu -- optimized Huffman tables (Annex K.2), kernel-format code words and the file header with its DHT
 // segments, one CTA per image. hist: [image][table][dc|ac][257] (hist_per_image = 0: one histogram for all).
