@@ -144,6 +144,7 @@ struct jpgb_encoder {
     PlanSig coef_sig{};
     const void *coef_pixels = nullptr;
     uint64_t coef_stride = 0;
+    float coef_ms[2] = {0.f, 0.f}; // with timing on: what the colour+DCT kernel and the histogram of that call took (added to the reusing call's stages)
     // replay of the launch sequence behind stage A as a CUDA graph (same settings, batch size and buffers)
     bool graphs_ok = true;
     struct CachedGraph {
@@ -401,6 +402,8 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
         pool_units = enc->caps[2];
     }
     bool coded = false;
+    const char *poison_env = std::getenv("JPGB_POISON_STREAM");
+    const bool poison = poison_env && poison_env[0] == '1';
     for (int attempt = 0;; ++attempt) {
         ucap = (ucap + kStuffChunk - 1) / kStuffChunk * kStuffChunk;
         const uint64_t n_pieces = ucap / kStuffChunk;
@@ -462,6 +465,8 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
             }
             {
                 StageTimer t(enc, 3);
+                // test hook: the stream starts out as all ones, so a byte that the kernels neither store nor zero shows in the output
+                if (poison) CK(cudaMemsetAsync(b.ustream, 0xFF, ucap + 64, st), "poison stream");
                 CK(launch_segment_leads(b, hp, n, st), "segment lead launch");
                 CK(launch_place_chunks(b, hp, n, st), "placement launch");
                 enc->launches += 2;
@@ -489,7 +494,7 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
             gk.sig = ck.sig;
             gk.n = n;
             gk.coder = coder;
-            gk.flags = (optimized ? 1u : 0u) | (piece_offsets ? 2u : 0u) | (given_hist ? 4u : 0u) | (uint32_t)hdr_stride << 8;
+            gk.flags = (optimized ? 1u : 0u) | (piece_offsets ? 2u : 0u) | (given_hist ? 4u : 0u) | (poison ? 8u : 0u) | (uint32_t)hdr_stride << 8;
             gk.misc[0] = (uint64_t)enc->hist.p;
             gk.misc[1] = (uint64_t)enc->huff.p;
             gk.misc[2] = (uint64_t)enc->hdr_parts.p;
@@ -1052,6 +1057,10 @@ static int encode_strip(jpgb_encoder *enc, const jpgb_params *p, const jpgb_stri
     enc->coef_tagged = false;
     if (rc2 != JPGB_OK) return rc2;
     timing_end(enc);
+    if (reuse && enc->timing) { // the stages that ran in the histogram call belong to this strip's encode
+        enc->last_ms[0] += enc->coef_ms[0];
+        enc->last_ms[1] += enc->coef_ms[1];
+    }
     std::memcpy(piece_offsets, pieces.data(), pieces.size() * 8);
     *d_bytes = enc->out.p;
     return JPGB_OK;
@@ -1086,12 +1095,19 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     ap.pixels = static_cast<const uint8_t *>(d_pixels);
     ap.coef = enc->coef.as<int16_t>();
     ap.image_stride = (size_t)p->width * strip->rows * bytes_per_pixel(p->color_type);
-    CK(launch_stage_a(ap, 1, st), "stage A launch");
+    timing_begin(enc);
+    {
+        StageTimer t(enc, 0);
+        CK(launch_stage_a(ap, 1, st), "stage A launch");
+    }
     const size_t hist_bytes = JPGB_HIST_WORDS * 4;
     CK(enc->hist.reserve(hist_bytes), "alloc histogram");
     CK(enc->h_hist.reserve(hist_bytes + 16), "alloc histogram (host)");
-    CK(cudaMemsetAsync(enc->hist.p, 0, hist_bytes, st), "clear histogram");
-    CK(launch_histogram(hp, enc->coef.as<int16_t>(), 1, enc->hist.as<uint32_t>(), st), "histogram launch");
+    {
+        StageTimer t(enc, 1);
+        CK(cudaMemsetAsync(enc->hist.p, 0, hist_bytes, st), "clear histogram");
+        CK(launch_histogram(hp, enc->coef.as<int16_t>(), 1, enc->hist.as<uint32_t>(), st), "histogram launch");
+    }
     enc->launches = 2;
     CK(cudaMemcpyAsync(enc->h_hist.p, enc->hist.p, hist_bytes, cudaMemcpyDeviceToHost, st), "download histogram");
     // DC of the first and of the last block of every component's true grid (the histogram chains DC differences
@@ -1110,6 +1126,9 @@ int jpgb_strip_histogram_device(jpgb_encoder *enc, const jpgb_params *p, const j
     enc->coef_pixels = d_pixels;
     enc->coef_stride = uint64_t(ap.image_stride);
     enc->coef_tagged = true;
+    timing_end(enc);
+    enc->coef_ms[0] = enc->timing ? enc->last_ms[0] : 0.f;
+    enc->coef_ms[1] = enc->timing ? enc->last_ms[1] : 0.f;
     return JPGB_OK;
 }
 

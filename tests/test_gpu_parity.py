@@ -638,6 +638,28 @@ def test_planar_warp_kernel_against_generic_kernel_and_oracle(sampling, monkeypa
             monkeypatch.delenv("JPGB_FORCE_GENERIC_STAGE_A")
 
 
+def test_unstuffed_stream_is_fully_written_without_a_clear(monkeypatch):
+    """The unstuffed stream is never cleared as a whole: chunks store the words they own and OR into the words they
+    share, which the lead kernel zeroes. With JPGB_POISON_STREAM=1 the buffer starts as all ones before every call, so any
+    byte that is neither stored nor zeroed corrupts the file."""
+    monkeypatch.setenv("JPGB_POISON_STREAM", "1")
+    cases = [("rgb", 333, 77, dict(quality=83, sampling=(2, 2))),
+             ("rgb", 640, 480, dict(quality=95, sampling=(2, 2), restart_interval=1)),
+             ("rgb", 641, 479, dict(quality=40, sampling=(2, 1), restart_interval=7, progressive_scans=5)),
+             ("luma", 1027, 517, dict(quality=99)),
+             ("luma", 5, 3, dict(quality=10, optimize_huffman=True)),
+             ("cmyk_as_ycck", 259, 131, dict(quality=75, sampling=(1, 1), optimize_huffman=True, restart_interval=3)),
+             ("ycbcr", 97, 75, dict(quality=60, sampling=(4, 1), restart_interval=2)),
+             ("rgb", 2048, 1024, dict(quality=90, sampling=(2, 2), progressive_scans=12, optimize_huffman=True))]
+    for color, w, h, cfg in cases:
+        img = _img(color, w, h, seed=5)
+        assert gpu_encode(img, w, h, color, cfg) == oracle_encode(img, w, h, color, cfg), (color, w, h, cfg)
+    import jpeg_encoder_b200 as je
+    frames = [_img("rgb", 320, 240, seed=60 + i) for i in range(9)]
+    cfg = dict(quality=88, sampling=(2, 2))
+    assert make_encoder(cfg).encode_batch(frames, 320, 240, je.ColorType.Rgb) == [oracle_encode(f, 320, 240, "rgb", cfg) for f in frames]
+
+
 def test_concurrent_contexts_on_threads():
     """One jpgb_encoder context per host thread (the reference's Encoder is Send, not shared): four threads
     encode different configurations at the same time on their own streams; every result must stay exact."""

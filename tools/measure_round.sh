@@ -30,4 +30,16 @@ for w in c4a c4b; do
   ncu --set full --clock-control none -k regex:stage_a_warp -s 2 -c 1 -o $O/${TAG}_stage_a_$w \
       python bench.py --workload $w --steps 2 --warmup 1 --no-cpu > $O/${TAG}_ncu_$w.log 2>&1
 done
+# the progressive coder (C5: blocks staged once for all scans -- dram__bytes_read per block) and the histogram of the optimized batch
+ncu --set full --clock-control none -k regex:encode_chunks -s 2 -c 1 -o $O/${TAG}_coder_c5 \
+    python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-c5 > $O/${TAG}_ncu_c5.log 2>&1
+ncu --set full --clock-control none -k regex:histogram_kernel -s 2 -c 1 -o $O/${TAG}_histogram_c3o \
+    python bench.py --workload c3o --batch 64 --steps 2 --warmup 1 --no-cpu --no-c5 > $O/${TAG}_ncu_c3o.log 2>&1
+# planar input: the plane kernel against the generic kernel
+python tools/planar_stage_time.py > $O/${TAG}_planar_stage_a.txt 2>&1
+# gpurun brings back at most 64 MiB: keep the raw metric pages (what tools/summarize_profiles.py reads), not the reports
+for r in $O/${TAG}_*.ncu-rep; do
+  ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null && rm -f $r
+done
+du -sh $O
 cut -c1-300 $O/${TAG}_bench_c3_1gpu.json

@@ -47,8 +47,12 @@ def ncu_raw(rep):
 
 
 def ncu_raw_all(rep):
-    """[(metrics, kernel name)] for every launch in the report"""
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """[(metrics, kernel name)] for every launch in the report (or in its exported raw page, <name>.raw.csv)"""
+    csv_path = rep[:-len(".ncu-rep")] + ".raw.csv"
+    if os.path.exists(csv_path):
+        out = open(csv_path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []
@@ -64,6 +68,10 @@ def ncu_raw_all(rep):
                     pass
         res.append((m, vals[hdr.index("Kernel Name")]))
     return res
+
+
+def have(rep):
+    return os.path.exists(rep) or os.path.exists(rep[:-len(".ncu-rep")] + ".raw.csv")
 
 
 def mbytes(m, key):
@@ -109,7 +117,7 @@ def main():
     frames = 64
     alg = 1920 * 1080 * 3 + 128 * 48960
     rep = os.path.join(SRC, tag + "_full.ncu-rep")
-    if os.path.exists(rep):
+    if have(rep):
         cmd = ("ncu --set full --clock-control none --import-source on -k 'regex:stage_a_warp|encode_chunks|place_chunks|stuff_scatter|count_ff' "
                "-s 10 -c 5 python bench.py --workload c3 --batch 64 --steps 2 --warmup 1 --no-cpu --no-c5")
         for m, name in ncu_raw_all(rep):
@@ -131,9 +139,26 @@ def main():
                 rec["warp_instructions_per_32_visits"] = m["smsp__inst_executed.sum"]["value"] / (visits / 32)
                 rec["algorithmic_bytes_per_frame"] = 128 * 48960
             json.dump(rec, open(os.path.join(DST, "%s_%s_ncu_summary.json" % (out_tag, short)), "w"), indent=1)
+    rep = os.path.join(SRC, tag + "_coder_c5.ncu-rep")
+    if have(rep):
+        m, name = ncu_raw_all(rep)[0]
+        blocks = (16384 // 8) ** 2 + 2 * (16384 // 16) ** 2  # 16384x16384 4:2:0: true grids of Y, Cb, Cr
+        json.dump({"kernel": name, "workload": "c5", "metrics": m, "blocks": blocks,
+                   "dram_bytes_read_per_block": mbytes(m, "dram__bytes_read.sum") / blocks,
+                   "note": "one 16384x16384 progressive image per launch (DC scan + AC bands of every component from one staging of each block), cold cache, under ncu"},
+                  open(os.path.join(DST, "%s_encode_chunks_c5_ncu_summary.json" % out_tag), "w"), indent=1)
+    rep = os.path.join(SRC, tag + "_histogram_c3o.ncu-rep")
+    if have(rep):
+        m, name = ncu_raw_all(rep)[0]
+        json.dump({"kernel": name, "workload": "c3o, 64 frames per launch", "metrics": m, "note": "cold cache, under ncu"},
+                  open(os.path.join(DST, "%s_histogram_kernel_ncu_summary.json" % out_tag), "w"), indent=1)
+    for f in ("planar_stage_a.txt", "compute_sanitizer_initcheck.txt"):
+        p = os.path.join(SRC, "%s_%s" % (tag, f))
+        if os.path.exists(p):
+            shutil.copy(p, os.path.join(DST, "%s_%s" % (out_tag, f)))
     for w in ("c4a", "c4b"):
         rep = os.path.join(SRC, "%s_stage_a_%s.ncu-rep" % (tag, w))
-        if os.path.exists(rep):
+        if have(rep):
             m, name = ncu_raw_all(rep)[0]
             json.dump({"kernel": name, "workload": w, "metrics": m, "note": "one 8192x8192 image per launch, cold cache, under ncu"},
                       open(os.path.join(DST, "%s_stage_a_%s_ncu_summary.json" % (out_tag, w)), "w"), indent=1)
