@@ -200,9 +200,15 @@ struct CoderSmem {
 //     the per-coefficient loop, which is where the time goes -- into the CTA's L2-resident scratch;
 //  4. prefix sum of the visits' bit counts, then every thread shifts its visit's words to their place in the
 //     chunk's bit string, assembled in shared memory and written to `pool` with coalesced 128-bit stores.
+// Resident CTAs per SM the register allocation aims at. The sequential coder needs 51 registers, which the allocation
+// granularity turns into 9 CTAs of 128 threads; capped at 48 (no spills) it is 10, as many as the shared memory allows:
+// 2.91 -> 2.80 ms on C3. The progressive variant (62 registers, 8 CTAs) spills when pushed to 10 (C5: 0.75 -> 0.78 ms) and
+// gains nothing at 9 (56 registers, no spill: 0.76 ms): it is left alone.
+__host__ __device__ constexpr int coder_min_ctas(int T, bool full) { return full && T >= 128 ? 1280 / T : 1024 / T; } // 48 / 64 registers
+
 // FULL: every scan of the plan covers the whole block (baseline and sequential modes).
 template <int T, bool FULL>
-__global__ void __launch_bounds__(T) encode_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P,
+__global__ void __launch_bounds__(T, coder_min_ctas(T, FULL)) encode_chunks_kernel(const __grid_constant__ EntropyBuffers b, const __grid_constant__ DevPlan P,
                                                           unsigned long long n_items) {
     using L = CoderSmem<T, FULL>;
     extern __shared__ __align__(16) unsigned char smem[];
