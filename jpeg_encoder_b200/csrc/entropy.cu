@@ -21,11 +21,16 @@
 //   [exclusive scan]     bit position of every chunk (one element per chunk, not per block)
 //   segment_len_kernel   segment -> lead + ceil(bits/8) + tail bytes
 //   [exclusive scan]     byte position of every segment in the unstuffed stream
-//   segment_lead_kernel  writes headers / RSTn / SOS / EOI, sets raw_mask
-//   place_chunks_kernel  streams every chunk from `pool` to its bit position (funnel shift), pad bits at segment end
+//   positions_kernel     small jobs: the three steps above (or the last two) in one single-CTA launch
+//   segment_lead_kernel  writes headers / RSTn / SOS / EOI, sets raw_mask; zeroes the stream words that two chunks
+//                        share (the stream is never cleared as a whole)
+//   place_chunks_kernel  streams every chunk from `pool` to its bit position (funnel shift): stores the words a chunk
+//                        owns, ORs into the shared ones; pad bits at segment end
 //   count_ff_kernel      4 KB piece of the stream -> number of data 0xFF bytes
-//   [exclusive scan]
-//   stuff_scatter_kernel copies every byte to its final place, inserting 0x00 after data 0xFF
+//   [exclusive scan]     skipped for short streams (the scatter CTAs add the counts up themselves)
+//   stuff_scatter_kernel copies every byte to its final place, inserting 0x00 after data 0xFF; extra CTAs work out
+//                        the file offsets and a strip's piece offsets
+//   histogram_kernel     optimized tables: symbol statistics of every image (same walk as the coder)
 #include <mutex>
 
 #include "kernels.h"
