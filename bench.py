@@ -41,11 +41,12 @@ WORKLOADS = {
     "c3o": (1920, 1080, "rgb", dict(quality=90, sampling=(2, 2), optimize_huffman=True), 1024,
             "batch of 1920x1080 RGB q90 4:2:0 frames with per-image optimized Huffman tables (histogram + Annex K.2 on the device)"),
     # formats outside the BASELINE configurations: verbatim / inverted byte formats on the warp kernel,
-    # and a factor-4 sampling on the generic kernel
+    # a factor-4 sampling and 4:4:4
     "x_ycbcr": (1920, 1080, "ycbcr", dict(quality=90, sampling=(2, 2)), 256, "batch of 1920x1080 YCbCr (verbatim) q90 4:2:0 baseline frames"),
     "x_cmyk": (4096, 4096, "cmyk", dict(quality=90, sampling=(2, 2)), 16, "batch of 4096x4096 CMYK (inverted) q90, K at 2x2, baseline frames"),
     "x_ycck": (4096, 4096, "ycck", dict(quality=90, sampling=(1, 1)), 16, "batch of 4096x4096 YCCK (verbatim) q90 4:4:4 baseline frames"),
     "x_rgb411": (1920, 1080, "rgb", dict(quality=90, sampling=(4, 1)), 256, "batch of 1920x1080 RGB q90 4:1:1 (factor 4: sequential scans)"),
+    "x_rgb444": (1920, 1080, "rgb", dict(quality=90, sampling=(1, 1)), 256, "batch of 1920x1080 RGB q90 4:4:4 baseline frames (the crate's default sampling for quality >= 90)"),
     "c4a": (8192, 8192, "luma", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,
             "1 x 8192x8192 grayscale q95 custom tables (BASELINE config 4a)"),
     "c4b": (8192, 8192, "cmyk_as_ycck", dict(quality=95, sampling=(1, 1), qtables="custom"), 1,

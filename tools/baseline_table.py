@@ -5,7 +5,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ROWS = [("c1", "C1"), ("c2", "C2"), ("c3", "C3"), ("c4a", "C4a"), ("c4a_x16", "C4a x16"), ("c4b", "C4b"), ("c5", "C5"), ("c5o", "C5o"), ("c3o", "C3o"),
-        ("x_ycbcr", "YCbCr 4:2:0"), ("x_ycck", "YCCK 4:4:4"), ("x_cmyk", "CMYK"), ("x_rgb411", "RGB 4:1:1")]
+        ("x_ycbcr", "YCbCr 4:2:0"), ("x_ycck", "YCCK 4:4:4"), ("x_cmyk", "CMYK"), ("x_rgb411", "RGB 4:1:1"), ("x_rgb444", "RGB 4:4:4")]
 
 
 def main():

@@ -14,7 +14,7 @@ python bench.py > $O/${TAG}_bench_c3_1gpu.json 2>> $O/${TAG}_bench.err
 for w in c1 c2 c4a c4b; do
   python bench.py --workload $w --cpu-seconds 6 > $O/${TAG}_bench_${w}_1gpu.json 2>> $O/${TAG}_bench.err
 done
-for w in c3o x_ycbcr x_cmyk x_ycck x_rgb411; do
+for w in c3o x_ycbcr x_cmyk x_ycck x_rgb411 x_rgb444; do
   python bench.py --workload $w --no-cpu > $O/${TAG}_bench_${w}_1gpu.json 2>> $O/${TAG}_bench.err
 done
 python bench.py --workload c4a --batch 16 --no-cpu > $O/${TAG}_bench_c4a_x16_1gpu.json 2>> $O/${TAG}_bench.err
@@ -30,6 +30,8 @@ for w in c4a c4b; do
   ncu --set full --clock-control none -k regex:stage_a_warp -s 2 -c 1 -o $O/${TAG}_stage_a_$w \
       python bench.py --workload $w --steps 2 --warmup 1 --no-cpu > $O/${TAG}_ncu_$w.log 2>&1
 done
+ncu --set full --clock-control none -k regex:stage_a_warp -s 2 -c 1 -o $O/${TAG}_stage_a_x_rgb444 \
+    python bench.py --workload x_rgb444 --batch 64 --steps 2 --warmup 1 --no-cpu --no-c5 > $O/${TAG}_ncu_x_rgb444.log 2>&1
 # the progressive coder (C5: blocks staged once for all scans -- dram__bytes_read per block) and the histogram of the optimized batch
 ncu --set full --clock-control none -k regex:encode_chunks -s 2 -c 1 -o $O/${TAG}_coder_c5 \
     python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-c5 > $O/${TAG}_ncu_c5.log 2>&1

@@ -156,11 +156,12 @@ def main():
         p = os.path.join(SRC, "%s_%s" % (tag, f))
         if os.path.exists(p):
             shutil.copy(p, os.path.join(DST, "%s_%s" % (out_tag, f)))
-    for w in ("c4a", "c4b"):
+    for w in ("c4a", "c4b", "x_rgb444"):
         rep = os.path.join(SRC, "%s_stage_a_%s.ncu-rep" % (tag, w))
         if have(rep):
             m, name = ncu_raw_all(rep)[0]
-            json.dump({"kernel": name, "workload": w, "metrics": m, "note": "one 8192x8192 image per launch, cold cache, under ncu"},
+            json.dump({"kernel": name, "workload": w, "metrics": m,
+                       "note": ("one 8192x8192 image per launch" if w.startswith("c4") else "64 frames of 1920x1080 per launch") + ", cold cache, under ncu"},
                       open(os.path.join(DST, "%s_stage_a_%s_ncu_summary.json" % (out_tag, w)), "w"), indent=1)
 
 

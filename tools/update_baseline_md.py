@@ -29,7 +29,7 @@ def row(f):
 
 
 def main():
-    r = {k: row(k + "_1gpu") for k in ("c1", "c2", "c3", "c4a", "c4a_x16", "c4b", "c5", "c5o", "c3o", "x_ycbcr", "x_ycck", "x_cmyk", "x_rgb411")}
+    r = {k: row(k + "_1gpu") for k in ("c1", "c2", "c3", "c4a", "c4a_x16", "c4b", "c5", "c5o", "c3o", "x_ycbcr", "x_ycck", "x_cmyk", "x_rgb411", "x_rgb444") if os.path.exists(P % (k + "_1gpu"))}
     T = ("| Config (BASELINE.json) | GPU MP/s, inputs in HBM, 1 B200 | ms / step | round 1 ms | e2e MP/s (pinned host pixels → host JPEG) | "
          "drop-in call MP/s, pageable / pinned input | CPU 1 thread MP/s | CPU all cores MP/s (cores) | stage-A GB/s | stage-A % of measured HBM peak (6541.1 GB/s) |\n"
          "|---|---|---|---|---|---|---|---|---|---|\n")
@@ -50,6 +50,8 @@ def main():
     T += line("YCCK 4:4:4 verbatim, 16 × 4096²", "x_ycck", "(generic kernel)")
     T += line("CMYK (inverted), K at 2×2, 16 × 4096²", "x_cmyk", "(generic kernel)")
     T += line("RGB 4:1:1 (factor 4, sequential scans), 256 × 1080p", "x_rgb411", "(generic kernel: 7.320)")
+    if "x_rgb444" in r:
+        T += line("RGB 4:4:4, 256 × 1080p", "x_rgb444", "—")
     path = os.path.join(ROOT, "BASELINE.md")
     s = open(path).read()
     a = s.index("| Config (BASELINE.json) | GPU MP/s")
