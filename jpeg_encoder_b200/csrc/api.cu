@@ -8,10 +8,13 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "../../include/jpegenc_b200.h"
+#include "copy_pool.h"
 #include "host.h"
 #include "kernels.h"
 
@@ -127,6 +130,7 @@ struct jpgb_encoder {
     PinnedBuf h_small, h_hist, h_tables, h_pieces, h_out, h_stage[2];
     cudaEvent_t ev_stage[2] = {};
     bool stage_busy[2] = {};
+    CopyPool copy_pool;
     int out_slot = 0; // which of out / out2 the next encode_device writes
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_slice;
@@ -598,40 +602,30 @@ int encode_device(jpgb_encoder *enc, const Plan &plan, const uint8_t *d_pixels, 
 // while the copy engine drains one, the host fills the other, so the DMA never waits for a page-locked bounce
 // inside the driver and the copy stays asynchronous.
 constexpr size_t kStageBytes = 16u << 20;
-// One core copies ~10 GB/s into pinned memory, a fifth of what the link takes: pieces of 8 MB and more are split over a few threads.
-void parallel_copy(void *dst, const uint8_t *src, size_t n) {
-    constexpr size_t kMinPerThread = 4u << 20; // starting a thread costs as much as copying ~1 MB: a 1080p frame is copied by the caller alone
-    unsigned threads = (unsigned)std::min<size_t>(4, n / kMinPerThread);
-    const unsigned hw = std::thread::hardware_concurrency();
-    if (hw && threads > hw) threads = hw;
-    if (threads <= 1) {
-        std::memcpy(dst, src, n);
-        return;
-    }
-    const size_t part = ((n / threads) + 63) & ~(size_t)63;
-    std::thread workers[3];
-    for (unsigned t = 1; t < threads; ++t) {
-        const size_t lo = t * part, hi = t + 1 == threads ? n : std::min(n, lo + part);
-        workers[t - 1] = std::thread([=] { if (lo < hi) std::memcpy(static_cast<uint8_t *>(dst) + lo, src + lo, hi - lo); });
-    }
-    std::memcpy(dst, src, std::min(part, n));
-    for (unsigned t = 1; t < threads; ++t) workers[t - 1].join();
-}
 cudaError_t upload_host(jpgb_encoder *enc, void *d_dst, const uint8_t *src, size_t bytes, cudaStream_t s) {
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError(); // an unregistered pointer may leave a sticky-free error code behind on older runtimes
     if (pinned || bytes <= 65536) return cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, s);
-    for (size_t off = 0, k = 0; off < bytes; off += kStageBytes, ++k) {
+    // pieces of 16 MB; an input of 16 .. 32 MB goes in two pieces (of whole MB) so that the DMA of the first one runs
+    // behind the copy of the second. Smaller inputs go in one piece: measured on a 1080p frame, two pieces and helper
+    // threads cost more in wake-ups (0.95 ms per call) than they save (0.84 ms with the caller copying alone).
+    size_t piece = kStageBytes;
+    if (bytes >= kStageBytes && bytes < 2 * kStageBytes) piece = ((bytes / 2 + (1u << 20) - 1) >> 20) << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("JPGB_COPY_THREADS")) hw = (unsigned)std::max(1, std::atoi(e)); // test hook: 1 = the caller alone
+    for (size_t off = 0, k = 0; off < bytes; off += piece, ++k) {
         const int b = (int)(k & 1);
-        const size_t n = std::min(kStageBytes, bytes - off);
+        const size_t n = std::min(piece, bytes - off);
         cudaError_t e = enc->h_stage[b].reserve(kStageBytes);
         if (e != cudaSuccess) return e;
         if (enc->stage_busy[b]) { // the DMA that last read this buffer must be done before the host overwrites it
             e = cudaEventSynchronize(enc->ev_stage[b]);
             if (e != cudaSuccess) return e;
         }
-        parallel_copy(enc->h_stage[b].p, src + off, n);
+        unsigned threads = (unsigned)std::min<size_t>(4, n >> 22); // at least 4 MB per thread
+        if (hw && threads > hw) threads = hw;
+        enc->copy_pool.copy(enc->h_stage[b].p, src + off, n, threads);
         e = cudaMemcpyAsync(static_cast<uint8_t *>(d_dst) + off, enc->h_stage[b].p, n, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return e;
         e = cudaEventRecord(enc->ev_stage[b], s);
